@@ -1,0 +1,52 @@
+// Device-initiated collectives over NVLink 5 / NVSwitch symmetric memory (comm_sm100.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kernels.h"
+
+namespace tds {
+
+constexpr int kMaxRanks = 8;
+constexpr int kCommMaxBlocks = 64;
+
+// One symmetric allocation as seen from this process: the same buffer on every rank, peer-mapped, plus (when the
+// fabric supports it) one multicast address that aliases all of them (NVLS).
+struct SymmBuf {
+  void* peer[kMaxRanks];   // peer[r] = rank r's copy mapped in THIS address space (peer[rank] is local)
+  void* mc;                // multicast address or nullptr
+};
+struct CommCtx {
+  uint32_t* flags[kMaxRanks];  // per-rank flag pads (symmetric, zero-initialised), >= kCommMaxBlocks*kMaxRanks*4 words
+  int rank, world;
+  int* error_flag;             // local sticky error word (timeouts)
+};
+
+// in-place sum all-reduce of buf[off, off+numel) (bf16, or fp32 when is_f32) across ranks; two-shot, one kernel
+void allreduce(const CommCtx& c, const SymmBuf& buf, int64_t elem_off, int64_t numel, bool is_f32, float scale,
+               int blocks, int channel, cudaStream_t s);
+// sum-reduce buf[off, off+numel) onto rank `dst` only (other ranks' copies untouched)
+void reduce_to(const CommCtx& c, const SymmBuf& buf, int64_t elem_off, int64_t numel, bool is_f32, int dst, float scale,
+               int blocks, int channel, cudaStream_t s);
+// replicate rank src's buf[off, off+numel) into every rank
+void broadcast_from(const CommCtx& c, const SymmBuf& buf, int64_t byte_off, int64_t nbytes, int src, int blocks,
+                    int channel, cudaStream_t s);
+// cross-GPU barrier (all blocks of all ranks)
+void barrier(const CommCtx& c, int channel, cudaStream_t s);
+
+// ZeRO-1/2 fused step on the ranges this rank owns: switch-reduced gradient (multimem.ld_reduce / P2P sum) ->
+// scale -> Adam on local fp32 master + moments -> new bf16 parameter multicast to every rank (multimem.st / P2P).
+constexpr int kMaxRanges = 400;
+struct OwnedRanges {
+  int64_t elem_off[kMaxRanges];   // offset in the flat param/grad buffers (elements, multiple of 8)
+  int64_t numel[kMaxRanges];      // multiple of 8 (padded)
+  int64_t state_off[kMaxRanges];  // offset in the compact local fp32 state arrays
+  int blk_start[kMaxRanges + 1];
+  int count;
+};
+void zero_fused_adam(const CommCtx& c, const SymmBuf& grads, const SymmBuf& params, const OwnedRanges& r, float* master,
+                     float* exp_avg, float* exp_avg_sq, const AdamHyper& h, bool bcast_params, int channel,
+                     cudaStream_t s);
+constexpr int kZeroChunk = 256 * 8 * 2;   // elements per CTA-iteration in zero_fused_adam
+
+}  // namespace tds

@@ -1,0 +1,292 @@
+// Device-initiated collectives for sm_100a over NVLink 5 / NVSwitch.
+//
+// Data path: every kernel here addresses peer memory directly — `multimem.ld_reduce` / `multimem.st` on the
+// NVLS multicast mapping (the switch reduces / replicates in-fabric), or plain 16-byte loads/stores on the
+// peer-mapped unicast pointers when no multicast object exists.  No NCCL on this path; torch.distributed is
+// used only once, to exchange the memory handles.  Synchronisation is device-side: per-block flag words in a
+// symmetric pad, set with release / consumed with acquire CAS at .sys scope (bounded spins: a dead peer turns
+// into a trap + diagnostic, never a silent GPU hang — SURVEY §5 "failure detection").
+//
+// Replaces the reference's per-tensor dist.all_reduce / dist.reduce / dist.broadcast + cuda.synchronize()
+// (tiny_deepspeed/core/zero/ddp/module.py:17-24, zero1/module.py:17-24, zero1/optim.py:20-34).
+#include <stdio.h>
+
+#include "comm.h"
+#include "common.cuh"
+
+namespace tds {
+
+constexpr int kCommThreads = 512;
+constexpr long long kSpinLimit = 20000000000LL;   // ~10 s of SM clocks
+
+// ---- .sys-scope flag primitives -----------------------------------------------------------------------
+TDS_DEVICE uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.global.release.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+TDS_DEVICE uint32_t cas_acquire_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
+  uint32_t old;
+  asm volatile("atom.global.acquire.sys.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "l"(p), "r"(cmp), "r"(val) : "memory");
+  return old;
+}
+
+TDS_DEVICE uint32_t* flag_slot(const CommCtx& c, int owner, int channel, int block, int peer) {
+  return c.flags[owner] + ((size_t)channel * kCommMaxBlocks + block) * kMaxRanks + peer;
+}
+
+TDS_DEVICE void spin_fail(const CommCtx& c, const char* what, int peer) {
+  printf("[tds comm] rank %d block %d: timeout in %s waiting on rank %d\n", c.rank, blockIdx.x, what, peer);
+  if (c.error_flag) *c.error_flag = 1;
+  asm volatile("trap;");
+}
+
+// Barrier between block b of every rank.  Thread r talks to rank r: raises the peer's slot, then consumes its own.
+TDS_DEVICE void block_barrier(const CommCtx& c, int channel) {
+  __syncthreads();
+  if (threadIdx.x < c.world) {
+    const int peer = threadIdx.x;
+    uint32_t* theirs = flag_slot(c, peer, channel, blockIdx.x, c.rank);
+    uint32_t* mine = flag_slot(c, c.rank, channel, blockIdx.x, peer);
+    long long t0 = clock64();
+    while (cas_release_sys(theirs, 0u, 1u) != 0u)
+      if (clock64() - t0 > kSpinLimit) spin_fail(c, "barrier(signal)", peer);
+    t0 = clock64();
+    while (cas_acquire_sys(mine, 1u, 0u) != 1u)
+      if (clock64() - t0 > kSpinLimit) spin_fail(c, "barrier(wait)", peer);
+  }
+  __syncthreads();
+}
+
+// ---- 16-byte multimem / peer accessors ---------------------------------------------------------------------
+TDS_DEVICE uint4 mm_ld_reduce_bf16(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+TDS_DEVICE uint4 mm_ld_reduce_f32(const void* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(mc) : "memory");
+  return v;
+}
+TDS_DEVICE void mm_st(void* mc, uint4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};"
+               ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+TDS_DEVICE uint4 ld16(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.relaxed.sys.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+TDS_DEVICE void st16(void* p, uint4 v) {
+  asm volatile("st.global.relaxed.sys.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+TDS_DEVICE void acc_bf16x8(float* acc, uint4 v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); acc[2 * i] += f.x; acc[2 * i + 1] += f.y; }
+}
+TDS_DEVICE uint4 pack_bf16x8(const float* f) {
+  uint4 v;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return v;
+}
+
+// sum over ranks of one 16-byte vector at byte offset `boff` — through the switch when possible
+template <bool F32>
+TDS_DEVICE void reduce_vec(const CommCtx& c, const SymmBuf& b, size_t boff, float* out /*8 (bf16) or 4 (f32)*/) {
+  if (b.mc) {
+    uint4 v = F32 ? mm_ld_reduce_f32((const char*)b.mc + boff) : mm_ld_reduce_bf16((const char*)b.mc + boff);
+    if (F32) { out[0] = __uint_as_float(v.x); out[1] = __uint_as_float(v.y); out[2] = __uint_as_float(v.z); out[3] = __uint_as_float(v.w); }
+    else { for (int i = 0; i < 8; ++i) out[i] = 0.f; acc_bf16x8(out, v); }
+  } else {
+    for (int i = 0; i < (F32 ? 4 : 8); ++i) out[i] = 0.f;
+    for (int r = 0; r < c.world; ++r) {
+      uint4 v = ld16((const char*)b.peer[(c.rank + r) % c.world] + boff);
+      if (F32) { out[0] += __uint_as_float(v.x); out[1] += __uint_as_float(v.y); out[2] += __uint_as_float(v.z); out[3] += __uint_as_float(v.w); }
+      else acc_bf16x8(out, v);
+    }
+  }
+}
+TDS_DEVICE void bcast_vec(const CommCtx& c, const SymmBuf& b, size_t boff, uint4 v) {
+  if (b.mc) mm_st((char*)b.mc + boff, v);
+  else for (int r = 0; r < c.world; ++r) st16((char*)b.peer[(c.rank + r) % c.world] + boff, v);
+}
+
+// =====================================================================================================
+// all-reduce (two-shot: reduce-scatter slice -> all-gather slice), in place
+// =====================================================================================================
+template <bool F32>
+__global__ void __launch_bounds__(kCommThreads) allreduce_kernel(const __grid_constant__ CommCtx c,
+                                                                const __grid_constant__ SymmBuf b, long long boff,
+                                                                long long nvec, float scale, int channel) {
+  block_barrier(c, channel);                        // every rank's contribution is in place
+  const long long per = (nvec + c.world - 1) / c.world;
+  const long long v0 = per * c.rank, v1 = (v0 + per < nvec) ? v0 + per : nvec;
+  for (long long i = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += (long long)gridDim.x * blockDim.x) {
+    float f[8];
+    reduce_vec<F32>(c, b, (size_t)(boff + i * 16), f);
+    uint4 o;
+    if (F32) { o.x = __float_as_uint(f[0] * scale); o.y = __float_as_uint(f[1] * scale); o.z = __float_as_uint(f[2] * scale); o.w = __float_as_uint(f[3] * scale); }
+    else { for (int j = 0; j < 8; ++j) f[j] *= scale; o = pack_bf16x8(f); }
+    bcast_vec(c, b, (size_t)(boff + i * 16), o);
+  }
+  __threadfence_system();
+  block_barrier(c, channel);                        // results visible everywhere before anyone returns
+}
+
+void allreduce(const CommCtx& c, const SymmBuf& buf, int64_t elem_off, int64_t numel, bool is_f32, float scale,
+               int blocks, int channel, cudaStream_t s) {
+  const int esz = is_f32 ? 4 : 2;
+  const long long boff = (long long)elem_off * esz, nvec = ((long long)numel * esz + 15) / 16;
+  if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
+  if (is_f32) allreduce_kernel<true><<<blocks, kCommThreads, 0, s>>>(c, buf, boff, nvec, scale, channel);
+  else allreduce_kernel<false><<<blocks, kCommThreads, 0, s>>>(c, buf, boff, nvec, scale, channel);
+}
+
+// =====================================================================================================
+// reduce to one rank / broadcast from one rank
+// =====================================================================================================
+template <bool F32>
+__global__ void __launch_bounds__(kCommThreads) reduce_to_kernel(const __grid_constant__ CommCtx c,
+                                                                const __grid_constant__ SymmBuf b, long long boff,
+                                                                long long nvec, int dst, float scale, int channel) {
+  block_barrier(c, channel);
+  if (c.rank == dst) {
+    char* local = (char*)b.peer[c.rank];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+      float f[8];
+      reduce_vec<F32>(c, b, (size_t)(boff + i * 16), f);
+      uint4 o;
+      if (F32) { o.x = __float_as_uint(f[0] * scale); o.y = __float_as_uint(f[1] * scale); o.z = __float_as_uint(f[2] * scale); o.w = __float_as_uint(f[3] * scale); }
+      else { for (int j = 0; j < 8; ++j) f[j] *= scale; o = pack_bf16x8(f); }
+      *reinterpret_cast<uint4*>(local + boff + i * 16) = o;
+    }
+  }
+  __threadfence_system();
+  block_barrier(c, channel);   // peers may now overwrite their (consumed) contributions
+}
+
+void reduce_to(const CommCtx& c, const SymmBuf& buf, int64_t elem_off, int64_t numel, bool is_f32, int dst, float scale,
+               int blocks, int channel, cudaStream_t s) {
+  const int esz = is_f32 ? 4 : 2;
+  const long long boff = (long long)elem_off * esz, nvec = ((long long)numel * esz + 15) / 16;
+  if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
+  if (is_f32) reduce_to_kernel<true><<<blocks, kCommThreads, 0, s>>>(c, buf, boff, nvec, dst, scale, channel);
+  else reduce_to_kernel<false><<<blocks, kCommThreads, 0, s>>>(c, buf, boff, nvec, dst, scale, channel);
+}
+
+__global__ void __launch_bounds__(kCommThreads) broadcast_kernel(const __grid_constant__ CommCtx c,
+                                                                const __grid_constant__ SymmBuf b, long long boff,
+                                                                long long nvec, int src, int channel) {
+  block_barrier(c, channel);   // nobody is still reading the old contents
+  if (c.rank == src) {
+    const char* local = (const char*)b.peer[c.rank];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (long long)gridDim.x * blockDim.x) {
+      uint4 v = *reinterpret_cast<const uint4*>(local + boff + i * 16);
+      if (b.mc) mm_st((char*)b.mc + boff + i * 16, v);
+      else for (int r = 1; r < c.world; ++r) st16((char*)b.peer[(c.rank + r) % c.world] + boff + i * 16, v);
+    }
+  }
+  __threadfence_system();
+  block_barrier(c, channel);
+}
+
+void broadcast_from(const CommCtx& c, const SymmBuf& buf, int64_t byte_off, int64_t nbytes, int src, int blocks,
+                    int channel, cudaStream_t s) {
+  if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
+  broadcast_kernel<<<blocks, kCommThreads, 0, s>>>(c, buf, (long long)byte_off, (long long)((nbytes + 15) / 16), src, channel);
+}
+
+__global__ void barrier_kernel(const __grid_constant__ CommCtx c, int channel) { block_barrier(c, channel); }
+void barrier(const CommCtx& c, int channel, cudaStream_t s) { barrier_kernel<<<1, 32, 0, s>>>(c, channel); }
+
+// =====================================================================================================
+// ZeRO-1/2 fused step: reduce(grad) -> scale -> Adam(master, m, v) -> multicast(param)
+// =====================================================================================================
+TDS_DEVICE int find_range(const int* blk_start, int count, int b) {
+  int lo = 0, hi = count - 1;
+  while (lo < hi) {
+    int mid = (lo + hi + 1) >> 1;
+    if (blk_start[mid] <= b) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(256) zero_fused_adam_kernel(const __grid_constant__ CommCtx c,
+                                                              const __grid_constant__ SymmBuf grads,
+                                                              const __grid_constant__ SymmBuf params,
+                                                              const __grid_constant__ OwnedRanges R,
+                                                              float* __restrict__ master, float* __restrict__ exp_avg,
+                                                              float* __restrict__ exp_avg_sq,
+                                                              const __grid_constant__ AdamHyper h, int bcast, int channel,
+                                                              int work_blocks) {
+  block_barrier(c, channel);                       // all ranks' gradients are complete
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const int step = *h.step_ptr;
+    s_bc[0] = 1.f - powf(h.beta1, (float)step);
+    s_bc[1] = rsqrtf(1.f - powf(h.beta2, (float)step));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2r = s_bc[1];
+  char* local_param = (char*)params.peer[c.rank];
+  for (int wb = blockIdx.x; wb < work_blocks; wb += gridDim.x) {
+    const int t = find_range(R.blk_start, R.count, wb);
+    const long long base = (long long)(wb - R.blk_start[t]) * kZeroChunk;
+    const long long n = R.numel[t];
+    const long long end = base + kZeroChunk < n ? base + kZeroChunk : n;
+    for (long long i = base + threadIdx.x * 8; i < end; i += 256 * 8) {
+      const size_t boff = (size_t)(R.elem_off[t] + i) * 2;
+      float g[8];
+      reduce_vec<false>(c, grads, boff, g);
+      const long long so = R.state_off[t] + i;
+      float w[8], m[8], v[8];
+      *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(master + so);
+      *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(master + so + 4);
+      *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(exp_avg + so);
+      *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(exp_avg + so + 4);
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(exp_avg_sq + so);
+      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(exp_avg_sq + so + 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gg = g[j] * h.grad_scale;
+        if (h.maximize) gg = -gg;
+        if (h.weight_decay != 0.f) {
+          if (h.decoupled) w[j] *= (1.f - h.lr * h.weight_decay);
+          else gg += h.weight_decay * w[j];
+        }
+        m[j] = h.beta1 * m[j] + (1.f - h.beta1) * gg;
+        v[j] = h.beta2 * v[j] + (1.f - h.beta2) * gg * gg;
+        w[j] -= (h.lr / bc1) * (m[j] / (sqrtf(v[j]) * bc2r + h.eps));
+      }
+      *reinterpret_cast<float4*>(master + so) = *reinterpret_cast<float4*>(w);
+      *reinterpret_cast<float4*>(master + so + 4) = *reinterpret_cast<float4*>(w + 4);
+      *reinterpret_cast<float4*>(exp_avg + so) = *reinterpret_cast<float4*>(m);
+      *reinterpret_cast<float4*>(exp_avg + so + 4) = *reinterpret_cast<float4*>(m + 4);
+      *reinterpret_cast<float4*>(exp_avg_sq + so) = *reinterpret_cast<float4*>(v);
+      *reinterpret_cast<float4*>(exp_avg_sq + so + 4) = *reinterpret_cast<float4*>(v + 4);
+      const uint4 o = pack_bf16x8(w);
+      if (bcast) bcast_vec(c, params, boff, o);
+      else *reinterpret_cast<uint4*>(local_param + boff) = o;
+    }
+  }
+  __threadfence_system();
+  block_barrier(c, channel);                       // new parameters visible on every rank
+}
+
+void zero_fused_adam(const CommCtx& c, const SymmBuf& grads, const SymmBuf& params, const OwnedRanges& r, float* master,
+                     float* exp_avg, float* exp_avg_sq, const AdamHyper& h, bool bcast_params, int channel,
+                     cudaStream_t s) {
+  const int work = r.blk_start[r.count];
+  // every rank launches the SAME grid (the barrier is per block index), whatever it owns
+  zero_fused_adam_kernel<<<kCommMaxBlocks, 256, 0, s>>>(c, grads, params, r, master, exp_avg, exp_avg_sq, h,
+                                                        bcast_params ? 1 : 0, channel, work);
+}
+
+}  // namespace tds

@@ -1,0 +1,87 @@
+// Shared device helpers for the sm_100a kernels of tiny_deepspeed_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+#define TDS_DEVICE __device__ __forceinline__
+
+namespace tds {
+
+constexpr int kWarp = 32;
+
+TDS_DEVICE float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+TDS_DEVICE float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// block-wide reductions through shared memory (blockDim.x multiple of 32, <= 1024)
+TDS_DEVICE float block_sum(float v, float* smem /* >= 32 floats */) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  v = (lane < nw) ? smem[lane] : 0.f;
+  return warp_sum(v);
+}
+TDS_DEVICE float block_max(float v, float* smem) {
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  v = (lane < nw) ? smem[lane] : -INFINITY;
+  return warp_max(v);
+}
+
+// 8 x bf16 <-> 8 x float through one 16-byte transaction
+struct alignas(16) bf16x8 {
+  __nv_bfloat162 v[4];
+};
+TDS_DEVICE void unpack8(const bf16x8& p, float* f) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 t = __bfloat1622float2(p.v[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+TDS_DEVICE bf16x8 pack8(const float* f) {
+  bf16x8 p;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) p.v[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+  return p;
+}
+TDS_DEVICE bf16x8 ld8(const __nv_bfloat16* p) { return *reinterpret_cast<const bf16x8*>(p); }
+TDS_DEVICE void st8(__nv_bfloat16* p, const bf16x8& v) { *reinterpret_cast<bf16x8*>(p) = v; }
+
+// generic scalar load/store as float for {float, bf16}
+template <typename T> TDS_DEVICE float ldf(const T* p);
+template <> TDS_DEVICE float ldf<float>(const float* p) { return *p; }
+template <> TDS_DEVICE float ldf<__nv_bfloat16>(const __nv_bfloat16* p) { return __bfloat162float(*p); }
+template <typename T> TDS_DEVICE void stf(T* p, float v);
+template <> TDS_DEVICE void stf<float>(float* p, float v) { *p = v; }
+template <> TDS_DEVICE void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+TDS_DEVICE float gelu_tanh(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float u = k0 * (x + k1 * x * x * x);
+  return 0.5f * x * (1.f + tanhf(u));
+}
+TDS_DEVICE float gelu_tanh_grad(float x) {
+  const float k0 = 0.7978845608028654f, k1 = 0.044715f;
+  float x2 = x * x;
+  float u = k0 * (x + k1 * x * x2);
+  float t = tanhf(u);
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x2);
+}
+
+}  // namespace tds

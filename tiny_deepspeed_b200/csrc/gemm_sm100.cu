@@ -1,0 +1,401 @@
+// Persistent warp-specialised tcgen05 GEMM for sm_100a (bf16 x bf16 -> fp32 in TMEM -> bf16/fp32).
+//
+//   D[b][m][n] = alpha * sum_k A(b,m,k) * B(b,n,k)      A: [M,K] K-major or [K,M] MN-major, same for B
+//
+// One kernel serves every GEMM of the GPT-2 step: Linear fwd (K-major/K-major), dX
+// (B = W consumed MN-major, no transpose copy), dW (both MN-major), and the batched attention products on
+// strided head views of the packed qkv buffer (4-D TMA maps: inner, row, head, batch).
+//
+// Structure (one CTA per SM, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor 128B-swizzled boxes -> smem ring, mbarrier expect_tx
+//   warp 1      MMA issuer: one lane issues tcgen05.mma (UMMA 128 x BN x 16), tcgen05.commit frees smem
+//               stages and publishes the accumulator; also owns the TMEM allocation (2 x BN columns)
+//   warps 2-5   epilogue: tcgen05.ld 32x32b (thread == accumulator row), fused bias / GELU / GELU' /
+//               residual / accumulate, 16-byte global stores; overlaps the next tile's MMAs through the
+//               double-buffered TMEM accumulator
+// Ragged edges come for free: TMA zero-fills out-of-bounds loads, the epilogue predicates its stores.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <mutex>
+#include <unordered_map>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+
+namespace tds {
+
+constexpr int BM = 128;       // UMMA M (cta_group::1)
+constexpr int BK = 64;        // one 128-byte swizzle row of bf16
+constexpr int UK = 16;        // UMMA K for 16-bit inputs
+constexpr int kThreads = 192;
+constexpr int kEpiWarp0 = 2;
+
+enum { EPI_NONE = 0, EPI_GELU_SAVE = 1, EPI_GELU_BWD = 2, EPI_RESIDUAL = 3 };
+
+struct GemmDev {
+  void* d; int d_f32; long long ldd, dbs1, dbs2;
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* aux; long long ld_aux;
+  int epi, accumulate; float alpha;
+  int M, N, K, batch, nb2;
+  int a_mn, b_mn;
+  int tri;
+  uint32_t idesc;
+};
+
+template <int BN> struct Cfg {
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kABytes = BM * BK * 2;   // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kSmem = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512 : powers of two
+};
+
+__device__ __forceinline__ void tile_k_range(const GemmDev& g, int m0, int nkb, int& kb0, int& kb1) {
+  kb0 = 0; kb1 = nkb;
+  if (g.tri == 2) { int e = (m0 + BM + BK - 1) / BK; kb1 = e < nkb ? e : nkb; }
+  else if (g.tri == 3) { kb0 = m0 / BK; }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ GemmDev g) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sA = smem_base;
+  const uint32_t sB = smem_base + C::kStages * C::kABytes;
+  const uint32_t sBar = sB + C::kStages * C::kBBytes;
+  // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
+  auto full_bar = [&](int s) { return sBar + 8u * s; };
+  auto empty_bar = [&](int s) { return sBar + 8u * (C::kStages + s); };
+  auto tfull_bar = [&](int s) { return sBar + 8u * (2 * C::kStages + s); };
+  auto tempty_bar = [&](int s) { return sBar + 8u * (2 * C::kStages + 2 + s); };
+  const uint32_t tmem_slot = sBar + 8u * (2 * C::kStages + 4);
+  uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
+  volatile uint32_t* tmem_slot_ptr =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_a);
+    ptx::prefetch_tmap(&tma_b);
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  const int m_tiles = (g.M + BM - 1) / BM;
+  const int n_tiles = (g.N + BN - 1) / BN;
+  const int tiles_per_batch = m_tiles * n_tiles;
+  const int total_tiles = tiles_per_batch * g.batch;
+  const int nkb = (g.K + BK - 1) / BK;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+        const int m0 = (r % m_tiles) * BM, n0 = (r / m_tiles) * BN;   // m fastest: neighbours share the B tile in L2
+        if (g.tri == 1 && n0 > m0 + BM - 1) continue;
+        const int b1 = b / g.nb2, b2 = b % g.nb2;
+        int kb0, kb1; tile_k_range(g, m0, nkb, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar(stage), C::kABytes + C::kBBytes);
+          const uint32_t a_dst = sA + stage * C::kABytes, b_dst = sB + stage * C::kBBytes;
+          const int k0 = kb * BK;
+          if (!g.a_mn) {
+            ptx::tma_load_4d(a_dst, &tma_a, full_bar(stage), k0, m0, b2, b1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 64; ++i)
+              ptx::tma_load_4d(a_dst + i * (BK * 128), &tma_a, full_bar(stage), m0 + 64 * i, k0, b2, b1);
+          }
+          if (!g.b_mn) {
+            ptx::tma_load_4d(b_dst, &tma_b, full_bar(stage), k0, n0, b2, b1);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i)
+              ptx::tma_load_4d(b_dst + i * (BK * 128), &tma_b, full_bar(stage), n0 + 64 * i, k0, b2, b1);
+          }
+          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    int stage = 0; uint32_t phase = 0;
+    int local = 0;
+    // descriptor strides: K-major: SBO = 1024 (8 rows x 128 B), per-UMMA_K advance 32 B;
+    //                     MN-major: LBO = BK*128 (next 64-wide MN group), SBO = 1024, advance 16 k-rows = 2048 B
+    const uint32_t a_lbo = g.a_mn ? BK * 128 : 16, b_lbo = g.b_mn ? BK * 128 : 16;
+    const uint32_t a_adv = g.a_mn ? UK * 128 : UK * 2, b_adv = g.b_mn ? UK * 128 : UK * 2;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int r = t % tiles_per_batch;
+      const int m0 = (r % m_tiles) * BM, n0 = (r / m_tiles) * BN;
+      if (g.tri == 1 && n0 > m0 + BM - 1) continue;
+      int kb0, kb1; tile_k_range(g, m0, nkb, kb0, kb1);
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      ++local;
+      ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + as * BN;
+      for (int kb = kb0; kb < kb1; ++kb) {
+        ptx::mbar_wait(full_bar(stage), phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_s = sA + stage * C::kABytes, b_s = sB + stage * C::kBBytes;
+#pragma unroll
+          for (int k = 0; k < BK / UK; ++k) {
+            const uint64_t da = ptx::make_smem_desc(a_s + k * a_adv, a_lbo, 1024);
+            const uint64_t db = ptx::make_smem_desc(b_s + k * b_adv, b_lbo, 1024);
+            ptx::mma_f16_ss(d_tmem, da, db, g.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs retire
+          if (kb == kb1 - 1) ptx::mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    int local = 0;
+    const bool vec_ok = (g.N % 8 == 0) && (g.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(g.d) & 15) == 0) &&
+                        (g.aux == nullptr || (g.ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0));
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int b = t / tiles_per_batch, r = t % tiles_per_batch;
+      const int m0 = (r % m_tiles) * BM, n0 = (r / m_tiles) * BN;
+      if (g.tri == 1 && n0 > m0 + BM - 1) continue;
+      const int b1 = b / g.nb2, b2 = b % g.nb2;
+      const int as = local & 1;
+      const uint32_t aphase = (local >> 1) & 1;
+      ++local;
+      ptx::mbar_wait(tfull_bar(as), aphase);
+      ptx::tc_fence_after();
+      const int m = m0 + q * 32 + lane;
+      const bool row_ok = m < g.M;
+      const long long d_off = (long long)b1 * g.dbs1 + (long long)b2 * g.dbs2 + (long long)m * g.ldd;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, raw);
+        ptx::tmem_ld_wait();
+        const int nb = n0 + c * 32;
+        if (row_ok && nb < g.N) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * g.alpha;
+          if (vec_ok && nb + 32 <= g.N) {
+            if (g.bias) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                float bf[8]; unpack8(ld8(g.bias + nb + j8 * 8), bf);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += bf[j];
+              }
+            }
+            if (g.epi != EPI_NONE) {
+              __nv_bfloat16* ap = g.aux + (long long)m * g.ld_aux + nb;
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                float af[8];
+                if (g.epi == EPI_GELU_SAVE) {
+                  bf16x8 pk = pack8(&v[j8 * 8]);
+                  st8(ap + j8 * 8, pk);
+                  unpack8(pk, af);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j8 * 8 + j] = gelu_tanh(af[j]);
+                } else {
+                  unpack8(ld8(ap + j8 * 8), af);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
+                }
+              }
+            }
+            if (g.d_f32) {
+              float* dp = reinterpret_cast<float*>(g.d) + d_off + nb;
+#pragma unroll
+              for (int j4 = 0; j4 < 8; ++j4) {
+                float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                if (g.accumulate) { float4 p = reinterpret_cast<float4*>(dp)[j4]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                reinterpret_cast<float4*>(dp)[j4] = o;
+              }
+            } else {
+              __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.d) + d_off + nb;
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8) {
+                if (g.accumulate) {
+                  float pf[8]; unpack8(ld8(dp + j8 * 8), pf);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += pf[j];
+                }
+                st8(dp + j8 * 8, pack8(&v[j8 * 8]));
+              }
+            }
+          } else {
+            // ragged / unaligned tail: scalar path
+            for (int j = 0; j < 32; ++j) {
+              const int n = nb + j;
+              if (n >= g.N) break;
+              float x = v[j];
+              if (g.bias) x += __bfloat162float(g.bias[n]);
+              if (g.epi == EPI_GELU_SAVE) {
+                __nv_bfloat16 pre = __float2bfloat16_rn(x);
+                g.aux[(long long)m * g.ld_aux + n] = pre;
+                x = gelu_tanh(__bfloat162float(pre));
+              } else if (g.epi == EPI_GELU_BWD) {
+                x *= gelu_tanh_grad(__bfloat162float(g.aux[(long long)m * g.ld_aux + n]));
+              } else if (g.epi == EPI_RESIDUAL) {
+                x += __bfloat162float(g.aux[(long long)m * g.ld_aux + n]);
+              }
+              if (g.d_f32) {
+                float* dp = reinterpret_cast<float*>(g.d) + d_off + n;
+                *dp = g.accumulate ? *dp + x : x;
+              } else {
+                __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.d) + d_off + n;
+                *dp = __float2bfloat16_rn(g.accumulate ? __bfloat162float(*dp) + x : x);
+              }
+            }
+          }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (wait::ld above): hand it back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+// =====================================================================================================
+// Host side
+// =====================================================================================================
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 4-D map over one bf16 operand: dims (inner, rows, nb2, nb1)
+static bool make_map(CUtensorMap* out, const GemmOperand& op, int rows_mn, int K, int nb1, int nb2, int box_rows_kmajor) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[4];
+  cuuint32_t box[4];
+  if (!op.mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows_mn; box[0] = BK; box[1] = (cuuint32_t)box_rows_kmajor; }
+  else              { dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = BK; }
+  dims[2] = (cuuint64_t)nb2; dims[3] = (cuuint64_t)nb1;
+  box[2] = 1; box[3] = 1;
+  const cuuint64_t row_bytes = (cuuint64_t)op.ld * 2;
+  cuuint64_t strides[3];
+  strides[0] = row_bytes;
+  strides[1] = nb2 > 1 ? (cuuint64_t)op.batch_stride2 * 2 : row_bytes * dims[1];
+  strides[2] = nb1 > 1 ? (cuuint64_t)op.batch_stride * 2 : strides[1] * (nb2 > 1 ? (cuuint64_t)nb2 : 1);
+  for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = row_bytes;
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "[tds] cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) ptr=%p\n",
+            (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+            (unsigned long long)dims[3], (unsigned long long)strides[0], (unsigned long long)strides[1],
+            (unsigned long long)strides[2], op.ptr);
+    return false;
+  }
+  return true;
+}
+
+static int g_num_sms = 0;
+
+int gemm_num_configs() { return 3; }   // BN = 64, 128, 256
+
+static int pick_config(const GemmParams& p) {
+  if (p.config >= 0 && p.config < 3) return p.config;
+  const long long mt = (p.M + BM - 1) / BM;
+  auto tiles = [&](int bn) { return mt * ((p.N + bn - 1) / bn) * p.batch; };
+  // largest tile that still gives (nearly) every SM work; small problems take the narrow tile for parallelism
+  if (tiles(256) >= g_num_sms) return 2;
+  if (tiles(128) * 10 >= (long long)g_num_sms * 6) return 1;
+  return tiles(64) > tiles(128) ? 0 : 1;
+}
+
+template <int BN>
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& g, int tiles, cudaStream_t s) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+    attr_done = true;
+  }
+  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+  gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, s>>>(ta, tb, g);
+}
+
+void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+  }
+  if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
+  const int cfg = pick_config(p);
+  const int bn = cfg == 0 ? 64 : (cfg == 1 ? 128 : 256);
+  const int nb2 = p.nbatch2 > 0 ? p.nbatch2 : 1;
+  const int nb1 = p.batch / nb2;
+  CUtensorMap ta, tb;
+  if (!make_map(&ta, p.a, p.M, p.K, nb1, nb2, BM) || !make_map(&tb, p.b, p.N, p.K, nb1, nb2, bn)) {
+    fprintf(stderr, "[tds] gemm: tensor map creation failed (M=%d N=%d K=%d)\n", p.M, p.N, p.K);
+    abort();
+  }
+  GemmDev g;
+  g.d = p.d; g.d_f32 = p.d_dtype == kF32; g.ldd = p.ldd; g.dbs1 = p.d_batch_stride; g.dbs2 = p.d_batch_stride2;
+  g.bias = reinterpret_cast<const __nv_bfloat16*>(p.bias);
+  g.aux = reinterpret_cast<__nv_bfloat16*>(p.aux); g.ld_aux = p.ld_aux;
+  g.epi = p.aux ? p.epi : EPI_NONE; g.accumulate = p.accumulate ? 1 : 0; g.alpha = p.alpha;
+  g.M = p.M; g.N = p.N; g.K = p.K; g.batch = p.batch; g.nb2 = nb2;
+  g.a_mn = p.a.mn_major; g.b_mn = p.b.mn_major; g.tri = p.tri;
+  g.idesc = make_idesc_bf16(BM, bn, p.a.mn_major, p.b.mn_major);
+  const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.batch;
+  if (cfg == 0) launch<64>(ta, tb, g, (int)tiles, stream);
+  else if (cfg == 1) launch<128>(ta, tb, g, (int)tiles, stream);
+  else launch<256>(ta, tb, g, (int)tiles, stream);
+}
+
+}  // namespace tds

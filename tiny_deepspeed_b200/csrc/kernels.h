@@ -1,0 +1,84 @@
+// Host-side launch API of the sm_100a kernels (raw pointers + stream; no torch types here).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tds {
+
+enum DType : int { kBF16 = 0, kF32 = 1 };
+
+// ---- GEMM (gemm_sm100.cu) ---------------------------------------------------------------------
+// D[b][m][n] = alpha * sum_k A(b,m,k) * B(b,n,k)  (+ epilogue).  bf16 operands, fp32 accumulate in TMEM.
+struct GemmOperand {
+  const void* ptr;      // bf16
+  int64_t ld;           // elements between consecutive rows of the stored 2-D matrix
+  int64_t batch_stride; // elements between batches (outer batch dim)
+  int64_t batch_stride2; // elements between inner batch index (batch = outer * nbatch2 + inner)
+  bool mn_major;        // false: stored [rows = M|N][K]; true: stored [K][rows = M|N]
+};
+struct GemmParams {
+  GemmOperand a, b;
+  void* d;  int d_dtype;  int64_t ldd, d_batch_stride, d_batch_stride2;
+  const void* bias;       // [N] bf16 or nullptr
+  void* aux;  int64_t ld_aux;   // bf16 [M,N] (no batch) or nullptr
+  int epi;                // EPI_* (see ops/__init__.py)
+  bool accumulate;        // D += result
+  float alpha;
+  int M, N, K, batch, nbatch2;
+  int config;             // tile configuration index, -1 = heuristic
+  int tri;                // causal structure: 0 none, 1 skip tiles above the diagonal (S, dP),
+                          // 2 K-range ends at the tile's last row (P.V, dS.K), 3 K-range starts at the tile's first row (P^T.dY, dS^T.Q)
+};
+void gemm_bf16(const GemmParams& p, cudaStream_t stream);
+int gemm_num_configs();
+
+// ---- elementwise / reductions (elementwise.cu) ----------------------------------------------------
+void layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd,
+                   int M, int N, float eps, int dtype, cudaStream_t s);
+int layernorm_bwd_scratch_rows();
+void layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
+                   const void* add, void* dx, float* scratch, void* dw, void* db, bool accumulate,
+                   int M, int N, int dtype, cudaStream_t s);
+void embedding_fwd(const int64_t* idx, const void* weight, const void* add, int add_rows, void* out,
+                   int ntok, int dim, int64_t vocab, int dtype, cudaStream_t s);
+void embedding_bwd(const int64_t* idx, const void* dy, void* dw, bool accumulate, int64_t padding_idx,
+                   int ntok, int dim, int64_t vocab, int dtype, cudaStream_t s);
+void softmax_causal_fwd(void* s_inout, int nmat, int T, float scale, cudaStream_t s);
+void softmax_causal_bwd(const void* p, void* dp_inout, int nmat, int T, float scale, cudaStream_t s);
+void xent_fwd(const void* logits, const int64_t* tgt, float* row_loss, float* lse, float* loss, int M, int V,
+              int dtype, cudaStream_t s);
+void xent_bwd(const void* logits, const int64_t* tgt, const float* lse, const float* gloss, void* dlogits,
+              int M, int V, int dtype, cudaStream_t s);
+void gelu_fwd(const void* x, void* y, int64_t n, int dtype, cudaStream_t s);
+void gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, cudaStream_t s);
+void colsum(const void* x, void* out, bool accumulate, int M, int N, int dtype, cudaStream_t s);
+
+// ---- optimizers (optim.cu) ---------------------------------------------------------------------------
+constexpr int kMaxTensorsPerLaunch = 320;
+struct TensorList {
+  void* p[kMaxTensorsPerLaunch];        // parameter (bf16 or fp32)
+  const void* g[kMaxTensorsPerLaunch];  // gradient (same dtype as p)
+  float* m[kMaxTensorsPerLaunch];       // exp_avg / momentum buffer (may be null for SGD w/o momentum)
+  float* v[kMaxTensorsPerLaunch];       // exp_avg_sq
+  float* master[kMaxTensorsPerLaunch];  // fp32 master weights or null
+  float* vmax[kMaxTensorsPerLaunch];    // amsgrad running max or null
+  int blk_start[kMaxTensorsPerLaunch + 1];
+  int64_t numel[kMaxTensorsPerLaunch];
+  int count;
+};
+struct AdamHyper {
+  float lr, beta1, beta2, eps, weight_decay, grad_scale;
+  int decoupled, maximize;
+  const int* step_ptr;  // device step counter (already incremented for this step)
+};
+struct SgdHyper {
+  float lr, momentum, dampening, weight_decay, grad_scale;
+  int nesterov, maximize;
+  const int* step_ptr;  // momentum buffer is initialised with g when *step_ptr == 1
+};
+void step_increment(int* step_ptr, cudaStream_t s);
+void adamw_multi(const TensorList& tl, const AdamHyper& h, int dtype, cudaStream_t s);
+void sgd_multi(const TensorList& tl, const SgdHyper& h, int dtype, cudaStream_t s);
+constexpr int kOptChunk = 256 * 8 * 4;   // elements per CTA in the multi-tensor kernels
+
+}  // namespace tds

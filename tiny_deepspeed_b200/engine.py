@@ -1,0 +1,100 @@
+"""TrainStep — the whole iteration (forward, backward, collectives, optimizer) as ONE CUDA graph.
+
+The reference workload is 1x1024 tokens per rank per step: on a B200 that is ~1 ms of math spread
+over hundreds of kernels, so the step is launch-bound unless it is replayed as a graph (SURVEY
+§7.4 item 6).  There is no tracing compiler here — just stream capture of the eager step, which
+works because every kernel of ours is stream-ordered, allocation-free and host-sync-free, the Adam
+step counter lives on the device, and the collectives are device-initiated.
+
+    step = TrainStep(model, optimizer)            # model: GPT2Model or a DDP/ZeroN wrapper
+    loss = step(idx, targets)                     # idx/targets: CPU (ideally pinned) or CUDA tensors
+
+Call semantics: copies the batch into static device buffers (H2D, async), replays the graph and
+returns the static loss tensor (fp32, on device).  On CPU, or with ``use_graph=False``, it simply
+runs the eager step — same numerics, used by the CPU test-suite.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+__all__ = ["TrainStep"]
+
+
+class TrainStep:
+    def __init__(self, model, optimizer, *, use_graph: Optional[bool] = None, warmup: int = 3,
+                 grad_sync: bool = True):
+        self.model = model
+        self.optimizer = optimizer
+        self.grad_sync = grad_sync
+        self.warmup = max(int(warmup), 1)
+        p = next((q for q in model.parameters() if q.numel() > 0), None)
+        self.device = p.device if p is not None else torch.device("cpu")
+        if use_graph is None:
+            use_graph = self.device.type == "cuda"
+        self.use_graph = bool(use_graph) and self.device.type == "cuda"
+        self.graph = None
+        self._static_idx = None
+        self._static_tgt = None
+        self._static_loss = None
+        self._seen = 0
+        self.steps = 0
+        self.launches_per_step = 0
+
+    # ------------------------------------------------------------------ eager step
+    def _eager(self, idx, targets):
+        from . import ops
+        n0 = ops.launches()
+        try:
+            return self._eager_impl(idx, targets)
+        finally:
+            self.launches_per_step = ops.launches() - n0   # kernels of ours per step (also what one graph replay runs)
+
+    def _eager_impl(self, idx, targets):
+        if hasattr(self.model, "require_backward_grad_sync"):
+            self.model.require_backward_grad_sync = self.grad_sync
+        _, loss = self.model(idx, targets)
+        loss.backward()
+        self.optimizer.step()
+        return loss.detach()
+
+    # ------------------------------------------------------------------ graph
+    def _stage(self, idx, targets):
+        if self._static_idx is None or self._static_idx.shape != idx.shape:
+            if self.graph is not None:
+                raise RuntimeError("TrainStep was captured for batch shape "
+                                   f"{tuple(self._static_idx.shape)}, got {tuple(idx.shape)}")
+            self._static_idx = torch.empty(idx.shape, dtype=torch.long, device=self.device)
+            self._static_tgt = torch.empty(targets.shape, dtype=torch.long, device=self.device)
+        self._static_idx.copy_(idx, non_blocking=True)
+        self._static_tgt.copy_(targets, non_blocking=True)
+
+    def _capture(self):
+        torch.cuda.synchronize(self.device)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._static_loss = self._eager(self._static_idx, self._static_tgt)
+        # capture only records: the captured step has not executed yet
+
+    def __call__(self, idx, targets):
+        self.steps += 1
+        if not self.use_graph:
+            if idx.device != self.device:
+                idx = idx.to(self.device, non_blocking=True)
+                targets = targets.to(self.device, non_blocking=True)
+            return self._eager(idx, targets)
+        self._stage(idx, targets)
+        if self.graph is None:
+            if self._seen < self.warmup:
+                # eager warm-up steps (real training steps) on a side stream, as graph capture requires
+                self._seen += 1
+                s = torch.cuda.Stream(self.device)
+                s.wait_stream(torch.cuda.current_stream(self.device))
+                with torch.cuda.stream(s):
+                    loss = self._eager(self._static_idx, self._static_tgt)
+                torch.cuda.current_stream(self.device).wait_stream(s)
+                return loss
+            self._capture()
+        self.graph.replay()
+        return self._static_loss

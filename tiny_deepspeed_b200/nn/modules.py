@@ -1,0 +1,303 @@
+"""Layers with policy-driven backward.  See package docstring."""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+import torch.nn as tnn
+
+from .. import ops
+from .policy import policy_of
+
+
+def _grad_of(policy, param, compute):
+    """Run ``compute(out, accumulate) -> grad`` into the policy's buffer and publish the result."""
+    out, acc = policy.grad_out(param)
+    g = compute(out, acc)
+    policy.grad_ready(param, g)
+
+
+# ----------------------------------------------------------------------------------------
+# Linear
+# ----------------------------------------------------------------------------------------
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, module, residual):
+        pol = policy_of(module)
+        w = pol.acquire(weight)
+        y = ops.linear_forward(x, w, bias, getattr(module, "runtime_tuner", None), residual=residual)
+        pol.release(weight, w)
+        ctx.module = module
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        module = ctx.module
+        pol = policy_of(module)
+        weight, bias = module.weight, module.bias
+        dy = dy.contiguous()
+        # dW first so its collective overlaps the dX GEMM (same ordering idea as the reference,
+        # tiny_deepspeed/core/zero/ddp/module.py:36-66, minus the cuda.synchronize()).
+        if weight.requires_grad:
+            _grad_of(pol, weight, lambda out, acc: ops.linear_weight_grad(
+                dy, x, weight, out=out, accumulate=acc, out_dtype=weight.dtype))
+        if bias is not None and bias.requires_grad:
+            _grad_of(pol, bias, lambda out, acc: ops.linear_bias_grad(dy, bias, out=out, accumulate=acc))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w = pol.acquire(weight, backward=True)
+            dx = ops.linear_input_grad(dy, w)
+            pol.release(weight, w)
+        return dx, None, None, None, (dy if ctx.has_res else None)
+
+
+class Linear(tnn.Linear):
+    """``nn.Linear`` with our GEMMs and a comm policy (reference module/linear.py:16-92)."""
+
+    policy = None
+    runtime_tuner = None
+
+    def forward(self, input, residual=None):
+        return _LinearFn.apply(input, self.weight, self.bias, self, residual)
+
+
+class _MLPFn(torch.autograd.Function):
+    """c_fc -> GELU(tanh) -> c_proj (+residual) as one autograd node so that GELU forward/backward
+    live in GEMM epilogues (EPI_GELU_SAVE on c_fc, EPI_GELU_BWD on c_proj's dX)."""
+
+    @staticmethod
+    def forward(ctx, x, fc, proj, residual):
+        pf, pp = policy_of(fc), policy_of(proj)
+        pre = torch.empty(*x.shape[:-1], fc.out_features, device=x.device, dtype=x.dtype)
+        w = pf.acquire(fc.weight)
+        act = ops.linear_forward(x, w, fc.bias, gelu_aux=pre)
+        pf.release(fc.weight, w)
+        w = pp.acquire(proj.weight)
+        y = ops.linear_forward(act, w, proj.bias, residual=residual)
+        pp.release(proj.weight, w)
+        ctx.fc, ctx.proj = fc, proj
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, pre, act)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, pre, act = ctx.saved_tensors
+        fc, proj = ctx.fc, ctx.proj
+        pf, pp = policy_of(fc), policy_of(proj)
+        dy = dy.contiguous()
+        _grad_of(pp, proj.weight, lambda out, acc: ops.linear_weight_grad(
+            dy, act, proj.weight, out=out, accumulate=acc, out_dtype=proj.weight.dtype))
+        if proj.bias is not None:
+            _grad_of(pp, proj.bias, lambda out, acc: ops.linear_bias_grad(dy, out=out, accumulate=acc))
+        w = pp.acquire(proj.weight, backward=True)
+        dpre = ops.linear_input_grad(dy, w, gelu_aux=pre)
+        pp.release(proj.weight, w)
+        _grad_of(pf, fc.weight, lambda out, acc: ops.linear_weight_grad(
+            dpre, x, fc.weight, out=out, accumulate=acc, out_dtype=fc.weight.dtype))
+        if fc.bias is not None:
+            _grad_of(pf, fc.bias, lambda out, acc: ops.linear_bias_grad(dpre, out=out, accumulate=acc))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            w = pf.acquire(fc.weight, backward=True)
+            dx = ops.linear_input_grad(dpre, w)
+            pf.release(fc.weight, w)
+        return dx, None, None, (dy if ctx.has_res else None)
+
+
+def fused_mlp(x, fc: Linear, proj: Linear, residual=None):
+    return _MLPFn.apply(x, fc, proj, residual)
+
+
+# ----------------------------------------------------------------------------------------
+# LayerNorm
+# ----------------------------------------------------------------------------------------
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, module, with_residual):
+        pol = policy_of(module)
+        w, b = pol.acquire(weight), pol.acquire(bias)
+        y, mean, rstd = ops.layernorm_fwd(x, w, b, module.eps)
+        pol.release(weight, w)
+        pol.release(bias, b)
+        ctx.module = module
+        ctx.with_residual = with_residual
+        ctx.save_for_backward(x, mean, rstd)
+        if with_residual:
+            # second output is x itself: the residual branch.  Its gradient comes back into this
+            # node and is folded into the dx kernel (no separate add kernel in backward).
+            return y, x.view_as(x)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy, dres=None):
+        x, mean, rstd = ctx.saved_tensors
+        module = ctx.module
+        pol = policy_of(module)
+        weight, bias = module.weight, module.bias
+        w = pol.acquire(weight, backward=True)
+        wo, wacc = pol.grad_out(weight)
+        bo, bacc = pol.grad_out(bias)
+        if wo is None or bo is None or wacc != bacc:
+            wo = bo = None
+            wacc = False
+        dx, dw, db = ops.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dw_out=wo, db_out=bo,
+                                       accumulate=wacc,
+                                       add_to_dx=dres.contiguous() if dres is not None else None)
+        pol.release(weight, w)
+        pol.grad_ready(weight, dw)
+        pol.grad_ready(bias, db)
+        return dx, None, None, None, None
+
+
+class LayerNorm(tnn.LayerNorm):
+    """Last-dim LayerNorm with affine weight+bias (same restrictions as reference
+    module/normalization.py:35-38,62-63)."""
+
+    policy = None
+    runtime_tuner = None
+
+    def _check(self):
+        if not self.elementwise_affine or self.bias is None:
+            raise NotImplementedError("LayerNorm requires elementwise_affine=True and bias=True")
+        if len(self.normalized_shape) != 1:
+            raise NotImplementedError("LayerNorm normalises the last dimension only")
+
+    def forward(self, input, with_residual: bool = False):
+        self._check()
+        return _LayerNormFn.apply(input, self.weight, self.bias, self, with_residual)
+
+
+# ----------------------------------------------------------------------------------------
+# Embedding
+# ----------------------------------------------------------------------------------------
+
+class _EmbeddingFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, weight, module, add):
+        pol = policy_of(module)
+        w = pol.acquire(weight)
+        y = ops.embedding_forward(idx, w, module.padding_idx, module.max_norm, module.norm_type,
+                                  module.scale_grad_by_freq, module.sparse, add=add)
+        pol.release(weight, w)
+        ctx.module = module
+        ctx.add_shape = None if add is None else tuple(add.shape)
+        ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        module = ctx.module
+        pol = policy_of(module)
+        weight = module.weight
+        dy = dy.contiguous()
+        _grad_of(pol, weight, lambda out, acc: ops.embedding_weight_grad(
+            idx, dy, weight, module.padding_idx, out=out, accumulate=acc,
+            shape=(module.num_embeddings, module.embedding_dim)))
+        dadd = None
+        if ctx.add_shape is not None and ctx.needs_input_grad[3]:
+            dadd = dy
+            while dadd.dim() > len(ctx.add_shape):
+                dadd = dadd[0] if dadd.shape[0] == 1 else dadd.sum(0)
+        return None, None, None, dadd
+
+
+class Embedding(tnn.Embedding):
+    """Embedding with dense gradient (reference module/embedding.py:15-98); ``add`` fuses ``+ pos``."""
+
+    policy = None
+    runtime_tuner = None
+
+    def forward(self, input, add=None):
+        return _EmbeddingFn.apply(input, self.weight, self, add)
+
+
+# ----------------------------------------------------------------------------------------
+# GELU / attention / loss
+# ----------------------------------------------------------------------------------------
+
+class _GeluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        ctx.save_for_backward(x)
+        return ops.gelu_forward(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (x,) = ctx.saved_tensors
+        return ops.gelu_backward(dy, x)
+
+
+class GELU(tnn.GELU):
+    """tanh-GELU (the model's only activation, reference example/model.py:94)."""
+
+    def forward(self, input):
+        if self.approximate != "tanh":
+            return super().forward(input)
+        return _GeluFn.apply(input)
+
+
+class _AttnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, qkv, n_head):
+        y, P = ops.causal_attention_forward(qkv, n_head)
+        ctx.n_head = n_head
+        ctx.save_for_backward(qkv, P)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        qkv, P = ctx.saved_tensors
+        return ops.causal_attention_backward(dy.contiguous(), qkv, P, ctx.n_head), None
+
+
+def causal_self_attention(qkv: torch.Tensor, n_head: int) -> torch.Tensor:
+    """Causal multi-head attention on the packed ``c_attn`` output ``[B,T,3C]`` -> ``[B,T,C]``."""
+    return _AttnFn.apply(qkv, n_head)
+
+
+class _XentFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets):
+        loss, lse = ops.cross_entropy_forward(logits, targets)
+        ctx.save_for_backward(logits, targets, lse)
+        return loss.to(torch.float32)
+
+    @staticmethod
+    def backward(ctx, g):
+        logits, targets, lse = ctx.saved_tensors
+        return ops.cross_entropy_backward(g, logits, targets, lse), None
+
+
+def cross_entropy(logits: torch.Tensor, targets: torch.Tensor) -> torch.Tensor:
+    """Mean token cross-entropy (fp32 scalar)."""
+    return _XentFn.apply(logits, targets)
+
+
+# ----------------------------------------------------------------------------------------
+# In-place adoption of plain torch.nn layers
+# ----------------------------------------------------------------------------------------
+
+def supported_modules():
+    """``{torch class: our class}`` (reference zero/ddp/wrapper.py:36-40 ``_supported_modules``)."""
+    return {tnn.Linear: Linear, tnn.LayerNorm: LayerNorm, tnn.Embedding: Embedding, tnn.GELU: GELU}
+
+
+def adopt(model: tnn.Module) -> tnn.Module:
+    """Turn every supported ``torch.nn`` layer of ``model`` into ours *in place* by re-classing the
+    instance: parameters keep their storage (works on meta tensors, costs nothing for XL) — the
+    reference re-creates each layer on CPU with a full random init and copies the weights back
+    (`tiny_deepspeed/core/zero/utils/wrapper.py:22-36`)."""
+    table = supported_modules()
+    for m in model.modules():
+        for src, dst in table.items():
+            if type(m) is src:
+                m.__class__ = dst
+                break
+    return model

@@ -1,0 +1,117 @@
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, Iterable, List, Tuple
+
+import torch
+
+
+class Optimizer:
+    """Named-parameter optimizer base (reference optim/base.py:7-26).
+
+    Subclasses implement ``_init_state(name, param)`` and ``_update(names)`` (one fused update
+    over the given parameter names).  ``owned(name)`` lets the sharded subclasses restrict state
+    and updates to the tensors this rank owns.
+    """
+
+    def __init__(self, named_parameters: Iterable[Tuple[str, torch.nn.Parameter]]):
+        self.parameters: "OrderedDict[str, torch.nn.Parameter]" = OrderedDict()
+        for name, p in named_parameters:
+            self.parameters[self._canon(name)] = p
+        self.state: Dict[str, Dict[str, torch.Tensor]] = OrderedDict()
+        self.step_count = 0
+        self.grad_scale = 1.0
+        for name, p in self.parameters.items():
+            if self.owned(name) and p.requires_grad:
+                self._ensure_state(name, p)
+
+    # DDP optimizers receive "module."-prefixed names, ZeRO ones un-prefixed: accept both.
+    @staticmethod
+    def _canon(name: str) -> str:
+        return name[len("module."):] if name.startswith("module.") else name
+
+    def owned(self, name: str) -> bool:
+        return True
+
+    # -- state ----------------------------------------------------------------------------
+    def _ensure_state(self, name, p):
+        if name not in self.state and p.device.type != "meta" and p.numel() > 0:
+            st = self._init_state(name, p)
+            if p.dtype in (torch.bfloat16, torch.float16):
+                st["master"] = p.detach().float().clone()
+            self.state[name] = st
+
+    def _init_state(self, name, p) -> Dict[str, torch.Tensor]:
+        return {}
+
+    # -- stepping ---------------------------------------------------------------------------
+    def _pending_sync(self):
+        """Wait (on stream) for gradient collectives still in flight."""
+        seen = set()
+        for p in self.parameters.values():
+            pol = getattr(p, "_tds_policy", None)
+            if pol is not None and id(pol) not in seen:
+                seen.add(id(pol))
+                pol.finish()
+
+    def _device_step(self, device):
+        """Device-resident step counter (int32): bumped by a 1-thread kernel so that a captured CUDA graph keeps
+        advancing Adam's bias correction on replay."""
+        if getattr(self, "_step_dev", None) is None or self._step_dev.device != device:
+            self._step_dev = torch.full((1,), self.step_count - 1, dtype=torch.int32, device=device)
+        from .. import ops
+        ops.ext().step_increment(self._step_dev)
+        ops.count_launch()
+        return self._step_dev
+
+    def step(self):
+        self._pending_sync()
+        self.step_count += 1
+        names: List[str] = []
+        for name, p in self.parameters.items():
+            if not self.owned(name) or p.grad is None:
+                continue
+            self._ensure_state(name, p)
+            names.append(name)
+        if names:
+            with torch.no_grad():
+                self._update(names)
+        self._post_update()
+        for p in self.parameters.values():
+            self._zero_grad(p)
+
+    def _post_update(self):
+        pass
+
+    def _update(self, names: List[str]):
+        raise NotImplementedError
+
+    def one_step(self, name: str, param=None):
+        """Update a single tensor (API parity with reference ``one_step(name, param)``)."""
+        with torch.no_grad():
+            self._update([self._canon(name)])
+
+    def _zero_grad(self, param):
+        param.grad = None
+
+    def zero_grad(self):
+        for p in self.parameters.values():
+            self._zero_grad(p)
+
+    # -- checkpointing (absent in the reference) ------------------------------------
+    def state_dict(self):
+        return {"step": self.step_count,
+                "state": {n: {k: v.detach().cpu() for k, v in st.items()} for n, st in self.state.items()},
+                "hyper": dict(self.hyper())}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        for n, st in sd["state"].items():
+            if n in self.parameters and self.owned(n):
+                p = self.parameters[n]
+                self._ensure_state(n, p)
+                for k, v in st.items():
+                    self.state[n][k].copy_(v.to(self.state[n][k].device))
+
+    def hyper(self):
+        return {}
