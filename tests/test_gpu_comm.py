@@ -1,0 +1,173 @@
+"""Multi-GPU: our symmetric-memory collectives vs torch.distributed (NCCL), and native-vs-dist mode equivalence
+(SURVEY §4 item 3).  Needs >= 2 GPUs."""
+from collections import OrderedDict
+
+import pytest
+import torch
+
+pytestmark = [pytest.mark.gpu, pytest.mark.multigpu]
+
+from gpu_dist_utils import run_gpu_distributed  # noqa: E402
+
+
+def _world():
+    return min(torch.cuda.device_count(), 8)
+
+
+def _collectives(rank, world):
+    import torch.distributed as dist
+    from tiny_deepspeed_b200.parallel import symm
+    dev = torch.device("cuda", rank)
+    comm = symm.Comm(dev)
+    out = {"multicast": None, "errors": []}
+    sizes = [1536, 3200, 768 * 768, 50304 * 768 + 64]          # 3 KB LN vector ... 77 MB embedding
+    total = sum((s + 63) // 64 * 64 for s in sizes)
+    st = symm.alloc(total * 2, dev)
+    out["multicast"] = st.has_multicast
+    flat = st.local.view(torch.bfloat16)
+    off = 0
+    for s in sizes:
+        g = torch.Generator(device=dev).manual_seed(1000 * rank + s % 997)
+        x = (torch.randn(s, device=dev, generator=g)).to(torch.bfloat16)
+        ref = x.float().clone()
+        dist.all_reduce(ref)                                     # fp32 NCCL reference
+        # --- all-reduce
+        flat[off:off + s].copy_(x)
+        comm.allreduce(st, off, s)
+        torch.cuda.synchronize()
+        err = (flat[off:off + s].float() - ref).abs().max().item()
+        if err > 0.02 * max(1.0, ref.abs().max().item()):
+            out["errors"].append(("allreduce", s, err))
+        # --- reduce to the last rank
+        flat[off:off + s].copy_(x)
+        torch.cuda.synchronize(); dist.barrier()
+        comm.reduce_to(st, off, s, world - 1)
+        torch.cuda.synchronize()
+        if rank == world - 1:
+            err = (flat[off:off + s].float() - ref).abs().max().item()
+            if err > 0.02 * max(1.0, ref.abs().max().item()):
+                out["errors"].append(("reduce_to", s, err))
+        else:
+            if not torch.equal(flat[off:off + s], x):
+                out["errors"].append(("reduce_to clobbered non-dst", s, 0))
+        # --- broadcast from rank 0
+        flat[off:off + s].copy_(x)
+        src = x.clone()
+        dist.broadcast(src, src=0)
+        torch.cuda.synchronize(); dist.barrier()
+        comm.broadcast(st, off * 2, s * 2, 0)
+        torch.cuda.synchronize()
+        if not torch.equal(flat[off:off + s], src):
+            out["errors"].append(("broadcast", s, 0))
+        off += (s + 63) // 64 * 64
+    # fp32 all-reduce
+    stf = symm.alloc(4096 * 4, dev)
+    f = stf.local.view(torch.float32)
+    f.copy_(torch.arange(4096, device=dev, dtype=torch.float32) * (rank + 1))
+    comm.allreduce(stf, 0, 4096, f32=True)
+    torch.cuda.synchronize()
+    want = torch.arange(4096, device=dev, dtype=torch.float32) * sum(range(1, world + 1))
+    if not torch.allclose(f, want):
+        out["errors"].append(("allreduce_f32", 4096, float((f - want).abs().max())))
+    return out
+
+
+def test_collective_kernels_match_nccl():
+    res = run_gpu_distributed(_collectives, world=_world())
+    for r in res:
+        assert r["errors"] == [], r
+    print("multicast:", res[0]["multicast"])
+
+
+def _train(rank, world, mode, backend, steps):
+    import torch.distributed as dist
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    from tiny_deepspeed_b200.parallel import materialize_
+    dev = torch.device("cuda", rank)
+    cfg = gpt2_config("tiny", n_layer=2, n_embd=256, n_head=4, vocab_size=2048, block_size=128)
+    with torch.device("meta"):
+        meta = GPT2Model(cfg)
+        parts, _ = tds.partition_tensors(OrderedDict(meta.named_parameters()), num_parts=world)
+    with torch.device("meta"):
+        model = GPT2Model(cfg).to(torch.bfloat16)
+    torch.cuda.reset_peak_memory_stats(dev)
+    if mode == "zero3":
+        model = tds.Zero3(model, parts, device=dev, init_seed=3, backend=backend)
+    else:
+        materialize_(model, device=dev, seed=3)
+        W = {"ddp": tds.DDP, "zero1": tds.Zero1, "zero2": tds.Zero2}[mode]
+        model = W(model, backend=backend) if mode == "ddp" else W(model, parts, backend=backend)
+    O = {"ddp": tds.DDPAdamW, "zero1": tds.Zero1AdamW, "zero2": tds.Zero2AdamW, "zero3": tds.Zero3AdamW}[mode]
+    if mode == "ddp":
+        opt = O(model.named_parameters(), lr=1e-3, weight_decay=0.1)
+    else:
+        opt = O(model.module.named_parameters(), lr=1e-3, weight_decay=0.1, param_part_table=parts,
+                ranks_map=[f"cuda:{i}" for i in range(world)])
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randint(0, cfg.vocab_size, (2, 128), generator=g).to(dev)
+    y = torch.randint(0, cfg.vocab_size, (2, 128), generator=g).to(dev)
+    losses, checks = [], {"backend": model.backend}
+    for i in range(steps):
+        model.require_backward_grad_sync = True
+        _, loss = model(x, y)
+        loss.backward()
+        if i == 0 and mode in ("zero2", "zero3"):
+            named = dict(model.module.named_parameters())
+            checks["nonowner_grad_none"] = all(p.grad is None for n, p in named.items() if parts[n] != rank)
+        if i == 0 and mode == "zero3":
+            checks["nonowner_param_freed"] = all(p.numel() == 0 for n, p in dict(model.module.named_parameters()).items()
+                                                 if parts[n] != rank)
+        opt.step()
+        l = loss.detach().float().clone()
+        dist.all_reduce(l)
+        losses.append(float(l) / world)
+    final = {}
+    for n, p in model.module.named_parameters():
+        if mode == "zero3":
+            t = p.detach().float().clone() if parts[n] == rank else torch.empty(p._tds_shape, device=dev)
+            dist.broadcast(t, src=parts[n])
+        else:
+            t = p.detach().float().clone()
+        final[n] = t.cpu()
+    return losses, final, checks
+
+
+@pytest.mark.parametrize("mode", ["ddp", "zero1", "zero2", "zero3"])
+def test_native_matches_dist_backend(mode):
+    world = _world()
+    nat = run_gpu_distributed(_train, world=world, args=(mode, "native", 5))
+    ref = run_gpu_distributed(_train, world=world, args=(mode, "dist", 5))
+    assert nat[0][2]["backend"] == "native" and ref[0][2]["backend"] == "dist"
+    for r in range(world):
+        assert all(v for k, v in nat[r][2].items() if k != "backend"), nat[r][2]
+    assert nat[0][0][-1] < nat[0][0][0]
+    assert nat[0][0] == pytest.approx(ref[0][0], rel=2e-2, abs=2e-2), (nat[0][0], ref[0][0])
+    for n in nat[0][1]:
+        a, b = nat[0][1][n], ref[0][1][n]
+        rel = (a - b).norm() / (b.norm() + 1e-9)
+        assert rel < 2e-2, (mode, n, float(rel))
+        for r in range(1, world):                                  # replicas agree bit-for-bit
+            assert torch.equal(nat[r][1][n], a), (mode, n, r)
+
+
+def _graph_ddp(rank, world):
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    cfg = gpt2_config("tiny", n_layer=2, n_embd=256, n_head=4, vocab_size=2048, block_size=128)
+    model = tds.DDP(GPT2Model(cfg).to(device=dev, dtype=torch.bfloat16), backend="native", bucket_bytes=1 << 20)
+    opt = tds.DDPAdamW(model.named_parameters(), lr=1e-3, weight_decay=0.1)
+    step = tds.TrainStep(model, opt, use_graph=True, warmup=2)
+    x = torch.randint(0, cfg.vocab_size, (2, 128), device=dev)
+    y = torch.randint(0, cfg.vocab_size, (2, 128), device=dev)
+    losses = [float(step(x, y)) for _ in range(8)]
+    return losses, step.graph is not None, model.policy.stats
+
+
+def test_ddp_native_under_cuda_graph():
+    res = run_gpu_distributed(_graph_ddp, world=_world())
+    losses, captured, stats = res[0]
+    assert captured and losses[-1] < losses[0]
+    assert stats["allreduce_launches"] > 0

@@ -1,0 +1,222 @@
+"""sm_100a kernels vs a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+from tiny_deepspeed_b200 import ops  # noqa: E402
+
+
+def _dev():
+    return torch.device("cuda", 0)
+
+
+def _rand(*shape, scale=1.0):
+    return (torch.randn(*shape, device=_dev(), dtype=torch.float32) * scale).to(torch.bfloat16)
+
+
+def _close(got, ref, rtol=2e-2, atol=2e-2):
+    torch.testing.assert_close(got.float(), ref.float(), rtol=rtol, atol=atol)
+
+
+def _ref_gemm(a, b, a_mn, b_mn):
+    A = a.float().transpose(-1, -2) if a_mn else a.float()
+    B = b.float().transpose(-1, -2) if b_mn else b.float()
+    return A @ B.transpose(-1, -2)
+
+
+def test_extension_is_loaded_from_tree():
+    import os
+    mod = ops.ext()
+    assert mod.__file__.endswith("tiny_deepspeed_b200/_C.so") and os.path.exists(mod.__file__)
+
+
+GEMM_SHAPES = [(128, 128, 64), (128, 64, 64), (256, 256, 128), (1024, 768, 768), (1024, 2304, 768), (1024, 768, 3072),
+               (1024, 3072, 768), (200, 136, 72), (1024, 1024, 64), (520, 50304, 256), (1000, 264, 1032)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+def test_gemm_layouts(M, N, K, a_mn, b_mn):
+    torch.manual_seed(M + N + K)
+    a = _rand(K, M) if a_mn else _rand(M, K)
+    b = _rand(K, N) if b_mn else _rand(N, K)
+    ref = _ref_gemm(a, b, a_mn, b_mn)
+    got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+    tol = 0.02 * math.sqrt(K)
+    torch.testing.assert_close(got.float(), ref, rtol=2e-2, atol=tol)
+    rel = (got.float() - ref).norm() / ref.norm()
+    assert rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2])
+def test_gemm_tile_configs_and_fp32_out(cfg):
+    a, b = _rand(384, 512), _rand(640, 512)
+    ref = a.float() @ b.float().t()
+    got = ops.gemm(a, b, config=cfg, out_dtype=torch.float32)
+    assert got.dtype == torch.float32
+    torch.testing.assert_close(got, ref, rtol=1e-3, atol=1e-2)
+    out = torch.ones(384, 640, device=_dev(), dtype=torch.float32)
+    ops.gemm(a, b, out=out, accumulate=True, alpha=0.5, config=cfg)
+    torch.testing.assert_close(out, 1 + 0.5 * ref, rtol=1e-3, atol=1e-2)
+
+
+def test_gemm_epilogues():
+    x, w, bias = _rand(1024, 768), _rand(3072, 768, scale=0.05), _rand(3072)
+    lin = x.float() @ w.float().t() + bias.float()
+    pre = torch.empty(1024, 3072, device=_dev(), dtype=torch.bfloat16)
+    act = ops.gemm(x, w, bias=bias, aux=pre, epi=ops.EPI_GELU_SAVE)
+    _close(pre, lin)
+    _close(act, F.gelu(pre.float(), approximate="tanh"))
+    dy = _rand(1024, 768)
+    w2 = _rand(768, 3072, scale=0.05)
+    dact = dy.float() @ w2.float()
+    p = pre.float().requires_grad_()
+    F.gelu(p, approximate="tanh").backward(dact)
+    got = ops.gemm(dy, w2, b_mn=True, aux=pre, epi=ops.EPI_GELU_BWD)
+    _close(got, p.grad, atol=5e-2)
+    res = _rand(1024, 3072)
+    got = ops.gemm(x, w, bias=bias, aux=res, epi=ops.EPI_RESIDUAL)
+    _close(got, lin + res.float(), atol=5e-2)
+    acc = _rand(1024, 3072)
+    want = acc.float() + (x.float() @ w.float().t())
+    ops.gemm(x, w, out=acc, accumulate=True)
+    _close(acc, want, atol=5e-2)
+
+
+def test_gemm_batched_strided_heads_and_tri():
+    B, T, nh, hs = 2, 256, 4, 64
+    C = nh * hs
+    qkv = _rand(B, T, 3 * C, scale=0.5)
+    q, k, v = (t.view(B, T, nh, hs).transpose(1, 2) for t in qkv.split(C, dim=2))
+    S = ops.gemm(q, k)
+    _close(S, q.float() @ k.float().transpose(-1, -2), atol=0.1)
+    St = torch.zeros_like(S)
+    ops.gemm(q, k, out=St, tri=1)
+    mask = torch.ones(T, T, device=_dev(), dtype=torch.bool).tril()
+    _close(St.float() * mask, (q.float() @ k.float().transpose(-1, -2)) * mask, atol=0.1)
+    P = torch.softmax((q.float() @ k.float().transpose(-1, -2)).masked_fill(~mask, float("-inf")) / 8.0, -1).to(torch.bfloat16)
+    y = torch.empty(B, T, C, device=_dev(), dtype=torch.bfloat16)
+    ops.gemm(P, v, b_mn=True, out=y.view(B, T, nh, hs).transpose(1, 2), tri=2)
+    _close(y.view(B, T, nh, hs).transpose(1, 2), P.float() @ v.float())
+    dv = ops.gemm(P, q, a_mn=True, b_mn=True, tri=3)
+    _close(dv, P.float().transpose(-1, -2) @ q.float(), atol=5e-2)
+
+
+@pytest.mark.parametrize("N", [768, 1024, 1280, 1600, 200])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_layernorm(N, dtype):
+    torch.manual_seed(N)
+    x = torch.randn(1024, N, device=_dev()).to(dtype)
+    w = (torch.rand(N, device=_dev()) + 0.5).to(dtype)
+    b = torch.randn(N, device=_dev()).to(dtype)
+    dy = torch.randn(1024, N, device=_dev()).to(dtype)
+    res = torch.randn(1024, N, device=_dev()).to(dtype)
+    xf = x.float().requires_grad_(); wf = w.float().requires_grad_(); bf = b.float().requires_grad_()
+    yr = F.layer_norm(xf, (N,), wf, bf, 1e-5)
+    yr.backward(dy.float())
+    y, mean, rstd = ops.layernorm_fwd(x, w, b, 1e-5)
+    tol = dict(rtol=2e-2, atol=3e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(y.float(), yr, **tol)
+    torch.testing.assert_close(mean, x.float().mean(-1), rtol=1e-4, atol=1e-4)
+    dx, dw, db = ops.layernorm_bwd(dy, x, w, mean, rstd, add_to_dx=res)
+    torch.testing.assert_close(dx.float(), xf.grad + res.float(), **tol)
+    big = dict(rtol=2e-2, atol=0.5) if dtype == torch.bfloat16 else dict(rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(dw.float(), wf.grad, **big)
+    torch.testing.assert_close(db.float(), bf.grad, **big)
+    dw2, db2 = dw.clone(), db.clone()
+    ops.layernorm_bwd(dy, x, w, mean, rstd, dw_out=dw2, db_out=db2, accumulate=True)
+    torch.testing.assert_close(dw2.float(), 2 * wf.grad, **big)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_embedding(dtype):
+    V, D = 50304, 768
+    w = torch.randn(V, D, device=_dev()).to(dtype)
+    idx = torch.randint(0, V, (2, 1024), device=_dev())
+    idx[0, :8] = 5                                     # repeated rows exercise the atomics
+    pos = torch.randn(1024, D, device=_dev()).to(dtype)
+    out = ops.embedding_forward(idx, w, add=pos)
+    torch.testing.assert_close(out.float(), F.embedding(idx, w).float() + pos.float(), rtol=1e-2, atol=2e-2)
+    dy = torch.randn(2, 1024, D, device=_dev()).to(dtype)
+    g = ops.embedding_weight_grad(idx, dy, w)
+    ref = torch.zeros(V, D, device=_dev()).index_add_(0, idx.view(-1), dy.view(-1, D).float())
+    torch.testing.assert_close(g.float(), ref, rtol=2e-2, atol=6e-2)
+
+
+def test_causal_softmax_and_attention():
+    B, T, nh, hs = 1, 1024, 12, 64
+    C = nh * hs
+    torch.manual_seed(0)
+    qkv = _rand(B, T, 3 * C, scale=0.7)
+    qf = qkv.float().requires_grad_()
+    q, k, v = (t.view(B, T, nh, hs).transpose(1, 2) for t in qf.split(C, dim=2))
+    ref = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, T, C)
+    dy = _rand(B, T, C)
+    ref.backward(dy.float())
+    y, P = ops.causal_attention_forward(qkv, nh)
+    _close(y, ref, atol=3e-2)
+    dqkv = ops.causal_attention_backward(dy, qkv, P, nh)
+    rel = (dqkv.float() - qf.grad).norm() / qf.grad.norm()
+    assert rel < 2e-2, rel
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+def test_cross_entropy(dtype):
+    M, V = 1024, 50304
+    l = (torch.randn(M, V, device=_dev()) * 2).to(dtype)
+    t = torch.randint(0, V, (M,), device=_dev())
+    lf = l.float().requires_grad_()
+    ref = F.cross_entropy(lf, t)
+    ref.backward()
+    loss, lse = ops.cross_entropy_forward(l, t)
+    torch.testing.assert_close(loss, ref, rtol=1e-4, atol=1e-4)
+    g = ops.cross_entropy_backward(torch.tensor(1.0, device=_dev()), l, t, lse)
+    torch.testing.assert_close(g.float(), lf.grad, rtol=2e-2, atol=1e-6 if dtype == torch.float32 else 1e-5)
+
+
+def test_gelu_and_colsum():
+    x = _rand(1024, 3072)
+    dy = _rand(1024, 3072)
+    _close(ops.gelu_forward(x), F.gelu(x.float(), approximate="tanh"))
+    xf = x.float().requires_grad_(); F.gelu(xf, approximate="tanh").backward(dy.float())
+    _close(ops.gelu_backward(dy, x), xf.grad)
+    _close(ops.linear_bias_grad(dy.view(2, 512, 3072)), dy.float().sum(0), atol=0.5)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32])
+@pytest.mark.parametrize("decoupled", [False, True])
+def test_fused_adam_multi_tensor(dtype, decoupled):
+    import tiny_deepspeed_b200 as tds
+    torch.manual_seed(0)
+    shapes = [(768, 768), (768,), (50304, 64), (3, 5), (1027,)]
+    ps = [torch.nn.Parameter(torch.randn(s, device=_dev()).to(dtype)) for s in shapes]
+    ref = [torch.nn.Parameter(p.detach().float().clone()) for p in ps]
+    opt = tds.AdamW([(f"p{i}", p) for i, p in enumerate(ps)], lr=1e-2, weight_decay=0.1, decoupled=decoupled)
+    ropt = (torch.optim.AdamW if decoupled else torch.optim.Adam)(ref, lr=1e-2, weight_decay=0.1)
+    for _ in range(4):
+        for p, r in zip(ps, ref):
+            g = torch.randn(p.shape, device=_dev())
+            p.grad = g.to(dtype)
+            r.grad = p.grad.float()
+        opt.step(); ropt.step()
+    for i, (p, r) in enumerate(zip(ps, ref)):
+        w = opt.state[f"p{i}"]["master"] if dtype == torch.bfloat16 else p
+        torch.testing.assert_close(w.float(), r, rtol=1e-4, atol=1e-5)
+        assert p.grad is None
+
+
+def test_fused_sgd_momentum():
+    import tiny_deepspeed_b200 as tds
+    p = torch.nn.Parameter(torch.randn(1000, 33, device=_dev()))
+    r = torch.nn.Parameter(p.detach().clone())
+    opt = tds.SGD([("p", p)], lr=0.05, momentum=0.9, weight_decay=0.01, nesterov=True)
+    ropt = torch.optim.SGD([r], lr=0.05, momentum=0.9, weight_decay=0.01, nesterov=True)
+    for _ in range(3):
+        g = torch.randn_like(p)
+        p.grad, r.grad = g.clone(), g.clone()
+        opt.step(); ropt.step()
+    torch.testing.assert_close(p, r, rtol=1e-5, atol=1e-6)

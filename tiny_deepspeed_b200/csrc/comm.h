@@ -36,9 +36,10 @@ void barrier(const CommCtx& c, int channel, cudaStream_t s);
 
 // ZeRO-1/2 fused step on the ranges this rank owns: switch-reduced gradient (multimem.ld_reduce / P2P sum) ->
 // scale -> Adam on local fp32 master + moments -> new bf16 parameter multicast to every rank (multimem.st / P2P).
-constexpr int kMaxRanges = 400;
+constexpr int kMaxRanges = 320;
 struct OwnedRanges {
-  int64_t elem_off[kMaxRanges];   // offset in the flat param/grad buffers (elements, multiple of 8)
+  int64_t elem_off[kMaxRanges];   // offset in the flat GRAD buffer (elements, multiple of 8)
+  int64_t pelem_off[kMaxRanges];  // offset in the PARAM buffer (differs from elem_off for ZeRO-3's owner-only layout)
   int64_t numel[kMaxRanges];      // multiple of 8 (padded)
   int64_t state_off[kMaxRanges];  // offset in the compact local fp32 state arrays
   int blk_start[kMaxRanges + 1];

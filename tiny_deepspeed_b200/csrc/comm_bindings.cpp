@@ -60,7 +60,7 @@ void py_barrier(const PyComm& c, int64_t channel) {
   check_launch("barrier");
 }
 
-// ranges: list of (elem_off, numel, state_off); all multiples of 8
+// ranges: list of (grad_elem_off, numel, state_off, param_elem_off); all multiples of 8
 int64_t py_zero_fused_adam(const PyComm& c, const PyBuf& grads, const PyBuf& params,
                            const std::vector<std::vector<int64_t>>& ranges, Tensor master, Tensor exp_avg,
                            Tensor exp_avg_sq, double lr, double b1, double b2, double eps, double wd, const Tensor& step,
@@ -77,8 +77,8 @@ int64_t py_zero_fused_adam(const PyComm& c, const PyBuf& grads, const PyBuf& par
     int cnt = 0, blk = 0;
     while (i < ranges.size() && cnt < kMaxRanges) {
       const auto& r = ranges[i];
-      TORCH_CHECK(r.size() == 3 && r[0] % 8 == 0 && r[1] % 8 == 0 && r[2] % 8 == 0, "ranges must be 8-element aligned");
-      R.elem_off[cnt] = r[0]; R.numel[cnt] = r[1]; R.state_off[cnt] = r[2];
+      TORCH_CHECK(r.size() == 4 && r[0] % 8 == 0 && r[1] % 8 == 0 && r[2] % 8 == 0 && r[3] % 8 == 0, "ranges must be 8-element aligned");
+      R.elem_off[cnt] = r[0]; R.numel[cnt] = r[1]; R.state_off[cnt] = r[2]; R.pelem_off[cnt] = r[3];
       R.blk_start[cnt] = blk;
       blk += (int)((r[1] + kZeroChunk - 1) / kZeroChunk);
       ++cnt; ++i;

@@ -272,8 +272,9 @@ __global__ void __launch_bounds__(256) zero_fused_adam_kernel(const __grid_const
       *reinterpret_cast<float4*>(exp_avg_sq + so) = *reinterpret_cast<float4*>(v);
       *reinterpret_cast<float4*>(exp_avg_sq + so + 4) = *reinterpret_cast<float4*>(v + 4);
       const uint4 o = pack_bf16x8(w);
-      if (bcast) bcast_vec(c, params, boff, o);
-      else *reinterpret_cast<uint4*>(local_param + boff) = o;
+      const size_t poff = (size_t)(R.pelem_off[t] + i) * 2;
+      if (bcast) bcast_vec(c, params, poff, o);
+      else *reinterpret_cast<uint4*>(local_param + poff) = o;
     }
   }
   __threadfence_system();

@@ -35,6 +35,9 @@ class Optimizer:
 
     # -- state ----------------------------------------------------------------------------
     def _ensure_state(self, name, p):
+        pol = getattr(p, "_tds_policy", None)
+        if pol is not None and getattr(pol, "is_native", False) and pol.owns_optimizer_state(self):
+            return  # the fused reduce->Adam->multicast kernel keeps compact fp32 state inside the policy
         if name not in self.state and p.device.type != "meta" and p.numel() > 0:
             st = self._init_state(name, p)
             if p.dtype in (torch.bfloat16, torch.float16):

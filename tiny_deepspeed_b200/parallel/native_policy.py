@@ -1,0 +1,258 @@
+"""NativePolicy — the B200 product path of DDP / ZeRO-1 / ZeRO-2 / ZeRO-3.
+
+Parameters and gradients live in flat *symmetric* buffers (same offsets on every rank, peer-mapped,
+multicast-bound).  The public ``{name: rank}`` map stays the user-facing artefact; here it is a set of
+views over those buffers.
+
+* **DDP** — backward GEMMs write dW straight into the symmetric gradient buffer; as soon as a bucket of
+  consecutive tensors is complete a two-shot NVLS all-reduce kernel (``multimem.ld_reduce`` +
+  ``multimem.st``) runs on the communication stream while backward continues.
+* **ZeRO-1/2** — one fused kernel per step on the owner: switch-reduced gradient → scale → Adam on
+  the local fp32 master/moments → bf16 parameter multicast to all ranks
+  (``csrc/comm_sm100.cu: zero_fused_adam_kernel``).  Non-owners never materialise ``param.grad``.
+* **ZeRO-3** — a tensor is resident on its owner only (the symmetric parameter buffer is sized for the
+  largest owner share, not for the model).  Consumers do not gather it: ``acquire`` hands the layer a
+  tensor that *aliases the owner's memory over NVLink*, and the tcgen05 GEMM's TMA producer streams the
+  weight tiles peer-to-peer straight into shared memory (all-gather fused into the GEMM, nothing staged
+  in local HBM).  Gradients are reduced to the owner by the same fused Adam kernel (no broadcast).
+
+Synchronisation is device-side (flag pads), the whole step is CUDA-graph capturable, and nothing here
+calls NCCL after construction.
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from typing import Dict, List, Optional
+
+import torch
+import torch.distributed as dist
+
+from .. import ops
+from ..nn.policy import CommPolicy
+from . import symm
+
+ALIGN = 64  # elements: every tensor starts on a 128-byte boundary of the flat buffers
+
+
+def _pad(n: int) -> int:
+    return (n + ALIGN - 1) // ALIGN * ALIGN
+
+
+class NativePolicy(CommPolicy):
+    is_native = True
+
+    def __init__(self, mode: str, model: torch.nn.Module, *, table: Optional[Dict[str, int]] = None, group=None,
+                 average: bool = False, bucket_bytes: int = 64 << 20, comm_blocks: int = 32):
+        self.mode = mode
+        self.name = f"native-{mode}"
+        self.group = group
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.average = average
+        self.scale = 1.0 / self.world if average else 1.0
+        self.bucket_bytes = bucket_bytes
+        self.comm_blocks = comm_blocks
+        named = [(n, p) for n, p in model.named_parameters()]
+        p0 = next(p for _, p in named if p.numel() > 0)
+        self.device, self.dtype = p0.device, p0.dtype
+        if self.dtype != torch.bfloat16:
+            raise NotImplementedError("native backend trains bf16 parameters (fp32 master weights live in the optimizer)")
+        self.table = table or {n: 0 for n, _ in named}
+        self.comm = symm.Comm(self.device, group)
+        self.comm_stream = torch.cuda.Stream(self.device)
+
+        # ---- layout ------------------------------------------------------------------------------
+        self.names: List[str] = [n for n, _ in named]
+        self.params: "OrderedDict[str, torch.nn.Parameter]" = OrderedDict(named)
+        self.shape = {n: tuple(getattr(p, "_tds_shape", p.shape)) for n, p in named}
+        self.numel = {n: int(torch.Size(self.shape[n]).numel()) for n in self.names}
+        self.goff, off = {}, 0                       # gradient buffer: every tensor, registration order
+        for n in self.names:
+            self.goff[n] = off
+            off += _pad(self.numel[n])
+        self.gtotal = off
+        self.poff = {}                               # parameter buffer
+        if mode == "zero3":
+            share = [0] * self.world                 # owner-only layout: offsets inside the owner's region
+            for n in self.names:
+                r = self.table[n]
+                self.poff[n] = share[r]
+                share[r] += _pad(self.numel[n])
+            self.ptotal = max(max(share), ALIGN)
+        else:
+            self.poff = dict(self.goff)
+            self.ptotal = self.gtotal
+        self.G = symm.alloc(self.gtotal * 2, self.device, group)
+        self.P = symm.alloc(self.ptotal * 2, self.device, group)
+        self.gflat = self.G.local.view(torch.bfloat16)
+        self.pflat = self.P.local.view(torch.bfloat16)
+
+        # ---- move parameters into the symmetric buffer (in place: the model keeps its Parameter objects) ----
+        with torch.no_grad():
+            for n, p in named:
+                resident = mode != "zero3" or self.table[n] == self.rank
+                view = self.pflat[self.poff[n]: self.poff[n] + self.numel[n]].view(self.shape[n])
+                if resident:
+                    if p.numel() == self.numel[n]:
+                        view.copy_(p.data)
+                    p.data = view
+                else:
+                    p.data = torch.empty(0, dtype=self.dtype, device=self.device)
+                p._tds_shape = self.shape[n]
+        self.gview = {n: self.gflat[self.goff[n]: self.goff[n] + self.numel[n]].view(self.shape[n]) for n in self.names}
+        self._name_of = {id(p): n for n, p in named}
+        torch.cuda.synchronize(self.device)
+        self.comm.barrier()
+
+        # ---- bucketing (DDP): backward produces tensors roughly in reverse registration order -----------
+        self.buckets: List[List[str]] = []
+        cur, cur_bytes = [], 0
+        for n in reversed(self.names):
+            cur.append(n)
+            cur_bytes += _pad(self.numel[n]) * 2
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {n: i for i, b in enumerate(self.buckets) for n in b}
+        self._reset_round()
+        self._accumulated = set()      # names holding un-synced micro-batch gradients
+        self._opt_state = None
+        self.stats = {"allreduce_launches": 0, "fused_steps": 0, "bytes": 0}
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _reset_round(self):
+        self._ready = [0] * len(self.buckets)
+        self._launched = [False] * len(self.buckets)
+        self._synced_any = False
+
+    def _owner(self, name):
+        return self.table[name]
+
+    # ------------------------------------------------------------------------------------------ gradients
+    def grad_out(self, param):
+        n = self._name_of[id(param)]
+        return self.gview[n], (n in self._accumulated)
+
+    def grad_ready(self, param, grad):
+        n = self._name_of[id(param)]
+        if grad.data_ptr() != self.gview[n].data_ptr():        # op ignored `out` (should not happen): copy in
+            if n in self._accumulated:
+                self.gview[n].add_(grad)
+            else:
+                self.gview[n].copy_(grad)
+        self._accumulated.add(n)
+        owner_like = self.mode in ("ddp", "zero1") or self._owner(n) == self.rank
+        if owner_like and param.numel() > 0:
+            param.grad = self.gview[n]
+        if not getattr(param, "bwd_sync", False):
+            return
+        param.bwd_sync = False
+        self._synced_any = True
+        if self.mode == "ddp" and self.world > 1:
+            b = self.bucket_of[n]
+            self._ready[b] += 1
+            # the all-reduce only touches the gradient buffer, so a bucket can go the moment its last dW is enqueued;
+            # it then runs on the comm stream underneath the remaining dX/dW GEMMs of backward
+            if self._ready[b] == len(self.buckets[b]) and not self._launched[b]:
+                self._launch_bucket(b)
+
+    def _launch_complete_buckets(self, flush=False):
+        for b, names in enumerate(self.buckets):
+            if self._launched[b]:
+                continue
+            if self._ready[b] == len(names) or (flush and self._ready[b] > 0):
+                self._launch_bucket(b)
+
+    def _launch_bucket(self, b):
+        names = self.buckets[b]
+        lo = min(self.goff[n] for n in names)
+        hi = max(self.goff[n] + _pad(self.numel[n]) for n in names)
+        cur = torch.cuda.current_stream(self.device)
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            self.comm.allreduce(self.G, lo, hi - lo, scale=self.scale, blocks=self.comm_blocks, channel=0)
+        self._launched[b] = True
+        self.stats["allreduce_launches"] += 1
+        self.stats["bytes"] += (hi - lo) * 2
+
+    def finish(self):
+        """Join the communication stream into the compute stream (no host synchronisation)."""
+        if self.mode == "ddp" and self.world > 1 and self._synced_any:
+            self._launch_complete_buckets(flush=True)
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+            self._accumulated.clear()
+            self._reset_round()
+        elif self.mode != "ddp" and self._synced_any and self._opt_state is None:
+            # generic (non-fused) optimizer: reduce every tensor onto its owner with our kernel, tensor by tensor
+            for n in self.names:
+                self.comm.reduce_to(self.G, self.goff[n], _pad(self.numel[n]), self._owner(n), scale=self.scale,
+                                    blocks=self.comm_blocks, channel=0)
+            self._accumulated.clear()
+            self._reset_round()
+
+    # ------------------------------------------------------------------------------------------ ZeRO-3 parameters
+    def acquire(self, param, *, backward=False):
+        if self.mode != "zero3" or self.world == 1:
+            return param
+        n = self._name_of[id(param)]
+        owner = self._owner(n)
+        if owner == self.rank:
+            return param.data
+        # alias of the OWNER's memory (NVLink peer mapping): the consuming kernel pulls it tile by tile
+        return self.P.peer(owner, self.shape[n], self.dtype, self.poff[n] * 2)
+
+    def release(self, param, full):
+        return
+
+    # ------------------------------------------------------------------------------------------ fused optimizer step
+    def owns_optimizer_state(self, opt) -> bool:
+        from ..optim.adamw import AdamW
+        return self.mode != "ddp" and self.world > 1 and isinstance(opt, AdamW) and not opt.amsgrad
+
+    def _ensure_opt_state(self, opt):
+        if self._opt_state is not None:
+            return self._opt_state
+        owned = [n for n in self.names if self.mode == "ddp" or self._owner(n) == self.rank]
+        soff, off = {}, 0
+        for n in owned:
+            soff[n] = off
+            off += _pad(self.numel[n])
+        total = max(off, ALIGN)
+        master = torch.zeros(total, dtype=torch.float32, device=self.device)
+        m = torch.zeros(total, dtype=torch.float32, device=self.device)
+        v = torch.zeros(total, dtype=torch.float32, device=self.device)
+        for n in owned:
+            src = self.pflat[self.poff[n]: self.poff[n] + self.numel[n]]
+            master[soff[n]: soff[n] + self.numel[n]].copy_(src.float())
+            # expose the compact state through the optimizer's public per-name dict (checkpointing, tests)
+            sl = slice(soff[n], soff[n] + self.numel[n])
+            opt.state[n] = {"exp_avg": m[sl].view(self.shape[n]), "exp_avg_sq": v[sl].view(self.shape[n]),
+                            "master": master[sl].view(self.shape[n])}
+        ranges = [[self.goff[n], _pad(self.numel[n]), soff[n], self.poff[n]] for n in owned]
+        self._opt_state = dict(master=master, m=m, v=v, ranges=ranges, owned=owned)
+        return self._opt_state
+
+    def fused_optimizer_step(self, opt) -> bool:
+        """ZeRO-1/2/3 + Adam: reduce -> Adam -> (multicast) in one kernel sequence.  Returns False when this
+        policy/optimizer pair must take the generic path."""
+        from ..optim.adamw import AdamW
+        if self.mode == "ddp" or self.world == 1 or not isinstance(opt, AdamW) or opt.amsgrad:
+            return False
+        if not self._synced_any:
+            return False
+        st = self._ensure_opt_state(opt)
+        opt.step_count += 1
+        step_dev = opt._device_step(self.device)
+        launches = ops.ext().comm_zero_fused_adam(
+            self.comm.ctx, self.G.buf, self.P.buf, st["ranges"], st["master"], st["m"], st["v"],
+            float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
+            bool(opt.decoupled), bool(opt.maximize), float(opt.grad_scale * self.scale),
+            self.mode != "zero3", 1)
+        ops.count_launch(int(launches))
+        self.stats["fused_steps"] += 1
+        for p in self.params.values():
+            p.grad = None
+        self._accumulated.clear()
+        self._reset_round()
+        return True
