@@ -220,3 +220,13 @@ def test_fused_sgd_momentum():
         p.grad, r.grad = g.clone(), g.clone()
         opt.step(); ropt.step()
     torch.testing.assert_close(p, r, rtol=1e-5, atol=1e-6)
+
+
+def test_splitk_lm_head_input_grad():
+    dy = _rand(1024, 50304, scale=0.1)
+    w = _rand(50304, 768, scale=0.1)
+    assert ops._splitk_factor(1024, 768, 50304) > 1
+    got = ops.linear_input_grad(dy, w)
+    ref = dy.float() @ w.float()
+    rel = (got.float() - ref).norm() / ref.norm()
+    assert rel < 5e-3, rel

@@ -211,6 +211,15 @@ void colsum_(const Tensor& x, Tensor& out, bool accumulate) {
   check_launch("colsum");
 }
 
+void sum_slices_(const Tensor& ws, Tensor& out) {
+  check_cuda(ws, "ws");
+  c10::cuda::CUDAGuard guard(ws.device());
+  TORCH_CHECK(ws.scalar_type() == at::kFloat && ws.is_contiguous() && out.scalar_type() == at::kBFloat16 && out.is_contiguous());
+  TORCH_CHECK(ws.numel() % out.numel() == 0);
+  sum_slices(ws.data_ptr<float>(), out.data_ptr(), out.numel(), (int)(ws.numel() / out.numel()), cur_stream());
+  check_launch("sum_slices");
+}
+
 // ---------------------------------------------------------------------------------------------------
 // optimizers
 // ---------------------------------------------------------------------------------------------------
@@ -300,6 +309,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gelu_fwd", &gelu_fwd_);
   m.def("gelu_bwd", &gelu_bwd_);
   m.def("colsum", &colsum_);
+  m.def("sum_slices", &sum_slices_);
   m.def("step_increment", &step_increment_);
   m.def("adamw_multi", &adamw_multi_);
   m.def("sgd_multi", &sgd_multi_);

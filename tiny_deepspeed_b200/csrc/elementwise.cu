@@ -89,7 +89,7 @@ void layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* 
 // and accumulating its dw/db partial column sums in SHARED memory (lane-private columns → no conflicts on
 // ownership); partials go to scratch[warp][2][N]; a second kernel reduces the scratch columns.
 constexpr int kLnBwdCtas = 148;
-int layernorm_bwd_scratch_rows() { return kLnBwdCtas; }
+int layernorm_bwd_scratch_rows() { return kLnBwdCtas; }  // >= rows used by either backward variant
 
 template <typename T>
 __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ x,
@@ -173,7 +173,7 @@ __global__ void ln_bwd_reduce_kernel(const float* __restrict__ scratch, T* __res
   stf(dst, a);
 }
 
-void layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, const void* add,
+void layernorm_bwd_generic(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, const void* add,
                    void* dx, float* scratch, void* dw, void* db, bool accumulate, int M, int N, int dtype,
                    cudaStream_t s) {
   const int ctas = kLnBwdCtas;
@@ -302,7 +302,7 @@ __global__ void __launch_bounds__(128) softmax_causal_fwd_kernel(__nv_bfloat16* 
   }
 }
 
-void softmax_causal_fwd(void* s_inout, int nmat, int T, float scale, cudaStream_t s) {
+void softmax_causal_fwd_generic(void* s_inout, int nmat, int T, float scale, cudaStream_t s) {
   const int nrows = nmat * T;
   softmax_causal_fwd_kernel<<<(nrows + 3) / 4, 128, 0, s>>>((__nv_bfloat16*)s_inout, nrows, T,
                                                             scale * 1.4426950408889634f);
@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(128) softmax_causal_bwd_kernel(const __nv_bflo
   }
 }
 
-void softmax_causal_bwd(const void* p, void* dp_inout, int nmat, int T, float scale, cudaStream_t s) {
+void softmax_causal_bwd_generic(const void* p, void* dp_inout, int nmat, int T, float scale, cudaStream_t s) {
   const int nrows = nmat * T;
   softmax_causal_bwd_kernel<<<(nrows + 3) / 4, 128, 0, s>>>((const __nv_bfloat16*)p, (__nv_bfloat16*)dp_inout, nrows,
                                                             T, scale);

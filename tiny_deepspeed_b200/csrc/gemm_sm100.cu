@@ -18,6 +18,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <mutex>
 #include <unordered_map>
 
@@ -32,6 +33,7 @@ constexpr int BK = 64;        // one 128-byte swizzle row of bf16
 constexpr int UK = 16;        // UMMA K for 16-bit inputs
 constexpr int kThreads = 192;
 constexpr int kEpiWarp0 = 2;
+constexpr uint32_t kStageBufBytes = 4096;   // one 32-row x 64-col bf16 slab, SWIZZLE_128B
 
 enum { EPI_NONE = 0, EPI_GELU_SAVE = 1, EPI_GELU_BWD = 2, EPI_RESIDUAL = 3 };
 
@@ -43,6 +45,8 @@ struct GemmDev {
   int M, N, K, batch, nb2;
   int a_mn, b_mn;
   int tri;
+  int tma_store;  // epilogue goes registers -> swizzled smem -> TMA store (bf16 out, no accumulate, aligned)
+  int dbg;      // TDS_GEMM_DBG bits (profiling only): 1 = no global stores, 2 = no MMA issue, 4 = no epilogue body
   uint32_t idesc;
 };
 
@@ -50,7 +54,7 @@ template <int BN> struct Cfg {
   static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kABytes = BM * BK * 2;   // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kSmem = kStages * (kABytes + kBBytes) + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmem = kStages * (kABytes + kBBytes) + 4 * 2 * 4096 /*epilogue staging*/ + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512 : powers of two
 };
 
@@ -63,13 +67,15 @@ __device__ __forceinline__ void tile_k_range(const GemmDev& g, int m0, int nkb, 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+            const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
             const __grid_constant__ GemmDev g) {
   using C = Cfg<BN>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + C::kStages * C::kABytes;
-  const uint32_t sBar = sB + C::kStages * C::kBBytes;
+  const uint32_t sStage = sB + C::kStages * C::kBBytes;              // 4 warps x 2 x (32 rows x 128 B), 1024-aligned
+  const uint32_t sBar = sStage + 4u * 2u * kStageBufBytes;
   // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (C::kStages + s); };
@@ -85,6 +91,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
+    if (g.tma_store) ptx::prefetch_tmap(&tma_d);
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
     ptx::fence_mbar_init();
@@ -165,7 +172,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = ptx::make_smem_desc(a_s + k * a_adv, a_lbo, 1024);
             const uint64_t db = ptx::make_smem_desc(b_s + k * b_adv, b_lbo, 1024);
-            ptx::mma_f16_ss(d_tmem, da, db, g.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (!(g.dbg & 2)) ptx::mma_f16_ss(d_tmem, da, db, g.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           ptx::mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs retire
           if (kb == kb1 - 1) ptx::mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
@@ -178,6 +185,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // ===================== epilogue warps =====================
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     int local = 0;
+    uint32_t sbuf_toggle = 0;
+    const uint32_t my_stage0 = sStage + (uint32_t)q * 2u * kStageBufBytes;   // two 4 KB staging buffers per warp
+    const bool gelu_save = g.epi == EPI_GELU_SAVE;
     const bool vec_ok = (g.N % 8 == 0) && (g.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(g.d) & 15) == 0) &&
                         (g.aux == nullptr || (g.ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0));
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -193,86 +203,147 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < g.M;
       const long long d_off = (long long)b1 * g.dbs1 + (long long)b2 * g.dbs2 + (long long)m * g.ldd;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      if (g.tma_store) {
+        // ---- coalesced path: registers -> 128B-swizzled smem slab (32 rows x 64 cols) -> TMA store ------------------
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + as * BN + c * 32, raw);
-        ptx::tmem_ld_wait();
-        const int nb = n0 + c * 32;
-        if (row_ok && nb < g.N) {
-          float v[32];
+        for (int slab = 0; slab < ((g.dbg & 4) ? 0 : BN / 64); ++slab) {
+          const int ns = n0 + slab * 64;
+          if (ns >= g.N) break;
+          uint32_t dbuf, abuf = 0;
+          if (gelu_save) { dbuf = my_stage0; abuf = my_stage0 + kStageBufBytes; if (lane == 0) ptx::bulk_wait_read<0>(); }
+          else { dbuf = my_stage0 + sbuf_toggle * kStageBufBytes; sbuf_toggle ^= 1u; if (lane == 0) ptx::bulk_wait_read<1>(); }
+          __syncwarp();
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * g.alpha;
-          if (vec_ok && nb + 32 <= g.N) {
-            if (g.bias) {
+          for (int half = 0; half < 2; ++half) {
+            uint32_t raw[32];
+            ptx::tmem_ld_32x32(t_row + slab * 64 + half * 32, raw);
+            ptx::tmem_ld_wait();
+            const int nb = ns + half * 32;
+            float v[32];
 #pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                float bf[8]; unpack8(ld8(g.bias + nb + j8 * 8), bf);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * g.alpha;
+#pragma unroll
+            for (int j8 = 0; j8 < 4; ++j8) {
+              const int nc = nb + j8 * 8;
+              const bool col_ok = nc + 8 <= g.N;       // N % 8 == 0 on this path
+              if (g.bias && col_ok) {
+                float bf[8]; unpack8(ld8(g.bias + nc), bf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += bf[j];
               }
-            }
-            if (g.epi != EPI_NONE) {
-              __nv_bfloat16* ap = g.aux + (long long)m * g.ld_aux + nb;
+              const uint32_t chunk = (uint32_t)(((half * 4 + j8) ^ (lane & 7)) * 16) + (uint32_t)lane * 128u;
+              if (gelu_save) {
+                bf16x8 pk = pack8(&v[j8 * 8]);
+                ptx::st_shared_16(abuf + chunk, pk);
+                float af[8]; unpack8(pk, af);
 #pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
+                for (int j = 0; j < 8; ++j) v[j8 * 8 + j] = gelu_tanh(af[j]);
+              } else if (g.epi != EPI_NONE) {
                 float af[8];
-                if (g.epi == EPI_GELU_SAVE) {
-                  bf16x8 pk = pack8(&v[j8 * 8]);
-                  st8(ap + j8 * 8, pk);
-                  unpack8(pk, af);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j8 * 8 + j] = gelu_tanh(af[j]);
-                } else {
-                  unpack8(ld8(ap + j8 * 8), af);
+                for (int j = 0; j < 8; ++j) af[j] = 0.f;
+                if (row_ok && col_ok) unpack8(ld8(g.aux + (long long)m * g.ld_aux + nc), af);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
+                for (int j = 0; j < 8; ++j)
+                  v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
+              }
+              ptx::st_shared_16(dbuf + chunk, pack8(&v[j8 * 8]));
+            }
+          }
+          ptx::fence_proxy_async();     // generic-proxy smem writes -> visible to the TMA (async proxy)
+          __syncwarp();
+          if (lane == 0 && m0 + q * 32 < g.M && !(g.dbg & 1)) {
+            ptx::tma_store_4d(&tma_d, dbuf, ns, m0 + q * 32, b2, b1);
+            if (gelu_save) ptx::tma_store_4d(&tma_aux, abuf, ns, m0 + q * 32, 0, 0);
+            ptx::bulk_commit();
+          }
+        }
+      } else {
+        // ---- direct path (fp32 output, accumulate, or unaligned): per-thread row segments --------------------------
+#pragma unroll 1
+        for (int c = 0; c < ((g.dbg & 4) ? 0 : BN / 32); ++c) {
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(t_row + c * 32, raw);
+          ptx::tmem_ld_wait();
+          const int nb = n0 + c * 32;
+          if (row_ok && nb < g.N && !(g.dbg & 1)) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * g.alpha;
+            if (vec_ok && nb + 32 <= g.N) {
+              if (g.bias) {
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                  float bf[8]; unpack8(ld8(g.bias + nb + j8 * 8), bf);
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += bf[j];
                 }
               }
-            }
-            if (g.d_f32) {
-              float* dp = reinterpret_cast<float*>(g.d) + d_off + nb;
+              if (g.epi != EPI_NONE) {
+                __nv_bfloat16* ap = g.aux + (long long)m * g.ld_aux + nb;
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
-                if (g.accumulate) { float4 p = reinterpret_cast<float4*>(dp)[j4]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
-                reinterpret_cast<float4*>(dp)[j4] = o;
-              }
-            } else {
-              __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.d) + d_off + nb;
+                for (int j8 = 0; j8 < 4; ++j8) {
+                  float af[8];
+                  if (g.epi == EPI_GELU_SAVE) {
+                    bf16x8 pk = pack8(&v[j8 * 8]);
+                    st8(ap + j8 * 8, pk);
+                    unpack8(pk, af);
 #pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                if (g.accumulate) {
-                  float pf[8]; unpack8(ld8(dp + j8 * 8), pf);
+                    for (int j = 0; j < 8; ++j) v[j8 * 8 + j] = gelu_tanh(af[j]);
+                  } else {
+                    unpack8(ld8(ap + j8 * 8), af);
 #pragma unroll
-                  for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += pf[j];
+                    for (int j = 0; j < 8; ++j)
+                      v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
+                  }
                 }
-                st8(dp + j8 * 8, pack8(&v[j8 * 8]));
-              }
-            }
-          } else {
-            // ragged / unaligned tail: scalar path
-            for (int j = 0; j < 32; ++j) {
-              const int n = nb + j;
-              if (n >= g.N) break;
-              float x = v[j];
-              if (g.bias) x += __bfloat162float(g.bias[n]);
-              if (g.epi == EPI_GELU_SAVE) {
-                __nv_bfloat16 pre = __float2bfloat16_rn(x);
-                g.aux[(long long)m * g.ld_aux + n] = pre;
-                x = gelu_tanh(__bfloat162float(pre));
-              } else if (g.epi == EPI_GELU_BWD) {
-                x *= gelu_tanh_grad(__bfloat162float(g.aux[(long long)m * g.ld_aux + n]));
-              } else if (g.epi == EPI_RESIDUAL) {
-                x += __bfloat162float(g.aux[(long long)m * g.ld_aux + n]);
               }
               if (g.d_f32) {
-                float* dp = reinterpret_cast<float*>(g.d) + d_off + n;
-                *dp = g.accumulate ? *dp + x : x;
+                float* dp = reinterpret_cast<float*>(g.d) + d_off + nb;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                  float4 o = make_float4(v[j4 * 4], v[j4 * 4 + 1], v[j4 * 4 + 2], v[j4 * 4 + 3]);
+                  if (g.accumulate) { float4 p = reinterpret_cast<float4*>(dp)[j4]; o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+                  reinterpret_cast<float4*>(dp)[j4] = o;
+                }
               } else {
-                __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.d) + d_off + n;
-                *dp = __float2bfloat16_rn(g.accumulate ? __bfloat162float(*dp) + x : x);
+                __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.d) + d_off + nb;
+#pragma unroll
+                for (int j8 = 0; j8 < 4; ++j8) {
+                  if (g.accumulate) {
+                    float pf[8]; unpack8(ld8(dp + j8 * 8), pf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += pf[j];
+                  }
+                  st8(dp + j8 * 8, pack8(&v[j8 * 8]));
+                }
+              }
+            } else {
+              // ragged / unaligned tail: scalar, statically indexed so v[] stays in registers
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const int n = nb + j;
+                if (n < g.N) {
+                  float x = v[j];
+                  if (g.bias) x += __bfloat162float(g.bias[n]);
+                  if (g.epi == EPI_GELU_SAVE) {
+                    __nv_bfloat16 pre = __float2bfloat16_rn(x);
+                    g.aux[(long long)m * g.ld_aux + n] = pre;
+                    x = gelu_tanh(__bfloat162float(pre));
+                  } else if (g.epi == EPI_GELU_BWD) {
+                    x *= gelu_tanh_grad(__bfloat162float(g.aux[(long long)m * g.ld_aux + n]));
+                  } else if (g.epi == EPI_RESIDUAL) {
+                    x += __bfloat162float(g.aux[(long long)m * g.ld_aux + n]);
+                  }
+                  if (g.d_f32) {
+                    float* dp = reinterpret_cast<float*>(g.d) + d_off + n;
+                    *dp = g.accumulate ? *dp + x : x;
+                  } else {
+                    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(g.d) + d_off + n;
+                    *dp = __float2bfloat16_rn(g.accumulate ? __bfloat162float(*dp) + x : x);
+                  }
+                }
               }
             }
           }
@@ -283,6 +354,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
     }
+    if (lane == 0) ptx::bulk_wait_read<0>();     // staging smem must outlive the last TMA store's reads
+    __syncwarp();
   }
 
   ptx::tc_fence_before();
@@ -358,14 +431,15 @@ static int pick_config(const GemmParams& p) {
 }
 
 template <int BN>
-static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmDev& g, int tiles, cudaStream_t s) {
+static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
+                   const GemmDev& g, int tiles, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
     attr_done = true;
   }
   const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, s>>>(ta, tb, g);
+  gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, s>>>(ta, tb, td, tx, g);
 }
 
 void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
@@ -391,11 +465,30 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   g.epi = p.aux ? p.epi : EPI_NONE; g.accumulate = p.accumulate ? 1 : 0; g.alpha = p.alpha;
   g.M = p.M; g.N = p.N; g.K = p.K; g.batch = p.batch; g.nb2 = nb2;
   g.a_mn = p.a.mn_major; g.b_mn = p.b.mn_major; g.tri = p.tri;
+  static const int dbg_env = getenv("TDS_GEMM_DBG") ? atoi(getenv("TDS_GEMM_DBG")) : 0;
+  g.dbg = dbg_env;
   g.idesc = make_idesc_bf16(BM, bn, p.a.mn_major, p.b.mn_major);
   const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.batch;
-  if (cfg == 0) launch<64>(ta, tb, g, (int)tiles, stream);
-  else if (cfg == 1) launch<128>(ta, tb, g, (int)tiles, stream);
-  else launch<256>(ta, tb, g, (int)tiles, stream);
+  // output through TMA (coalesced 128-byte rows) whenever the layout allows it
+  CUtensorMap td = ta, tx = ta;
+  g.tma_store = 0;
+  static const int no_tma_store = getenv("TDS_GEMM_DIRECT_STORE") ? atoi(getenv("TDS_GEMM_DIRECT_STORE")) : 0;
+  const bool aligned = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) && (p.N % 8 == 0) &&
+                       (p.d_batch_stride % 8 == 0) && (p.d_batch_stride2 % 8 == 0);
+  if (!no_tma_store && p.d_dtype == kBF16 && !p.accumulate && aligned) {
+    GemmOperand od{p.d, p.ldd, p.d_batch_stride, p.d_batch_stride2, false};
+    bool ok = make_map(&td, od, p.M, p.N, nb1, nb2, 32);
+    if (ok && g.epi == EPI_GELU_SAVE) {
+      GemmOperand oa{p.aux, p.ld_aux, 0, 0, false};
+      ok = (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && make_map(&tx, oa, p.M, p.N, 1, 1, 32);
+    }
+    if (ok && g.epi != EPI_NONE && g.epi != EPI_GELU_SAVE)
+      ok = (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
+    g.tma_store = ok ? 1 : 0;
+  }
+  if (cfg == 0) launch<64>(ta, tb, td, tx, g, (int)tiles, stream);
+  else if (cfg == 1) launch<128>(ta, tb, td, tx, g, (int)tiles, stream);
+  else launch<256>(ta, tb, td, tx, g, (int)tiles, stream);
 }
 
 }  // namespace tds

@@ -52,6 +52,7 @@ void xent_bwd(const void* logits, const int64_t* tgt, const float* lse, const fl
 void gelu_fwd(const void* x, void* y, int64_t n, int dtype, cudaStream_t s);
 void gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, cudaStream_t s);
 void colsum(const void* x, void* out, bool accumulate, int M, int N, int dtype, cudaStream_t s);
+void sum_slices(const float* ws, void* out_bf16, int64_t n, int S, cudaStream_t s);   // split-K fold (fast_rows.cu)
 
 // ---- optimizers (optim.cu) ---------------------------------------------------------------------------
 constexpr int kMaxTensorsPerLaunch = 320;

@@ -56,6 +56,19 @@ TDS_PTX void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, 
       : "memory");
 }
 
+TDS_PTX void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+TDS_PTX void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> TDS_PTX void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+template <typename T16> TDS_PTX void st_shared_16(uint32_t addr, const T16& v) {
+  static_assert(sizeof(T16) == 16, "16-byte payload");
+  const uint4 u = *reinterpret_cast<const uint4*>(&v);
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------------
 TDS_PTX void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

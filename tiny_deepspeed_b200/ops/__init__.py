@@ -118,6 +118,34 @@ def _flat2d(x):
     return x.reshape(-1, x.shape[-1])
 
 
+def _splitk_factor(M, N, K, sms=148):
+    """Split the reduction when a long-K GEMM has too few output tiles to fill the chip (lm_head dX: 48 tiles, K=50304)."""
+    tiles = ((M + 127) // 128) * ((N + 127) // 128)
+    if tiles * 2 > sms:
+        return 1
+    want = max(1, (2 * sms) // tiles)
+    for s in range(min(want, 16), 1, -1):
+        if K % (64 * s) == 0:
+            return s
+    return 1
+
+
+def gemm_splitk(a, b, splits):
+    """``D = A[M,K] . B[K,N]`` (A K-major, B MN-major) with K cut into ``splits`` batches: one batched tcgen05 launch
+    into fp32 slices + one fold kernel.  Used where K is huge and M x N small."""
+    M, K = a.shape
+    N = b.shape[1]
+    kc = K // splits
+    a3 = a.view(M, splits, kc).transpose(0, 1)          # [S, M, K/S] strided view, no copy
+    b3 = b.view(splits, kc, N)                          # [S, K/S, N]
+    ws = torch.empty(splits, M, N, device=a.device, dtype=torch.float32)
+    gemm(a3, b3, b_mn=True, out=ws)
+    out = torch.empty(M, N, device=a.device, dtype=a.dtype)
+    ext().sum_slices(ws, out)
+    count_launch()
+    return out
+
+
 def linear_forward(input, weight, bias=None, runtime_tuner=None, *, gelu_aux=None, residual=None):
     """``Y = X @ W^T (+ b)`` (reference ops/linear.py:50-54).
 
@@ -143,6 +171,8 @@ def linear_input_grad(grad_output, weight, runtime_tuner=None, *, gelu_aux=None)
     dy2 = _flat2d(grad_output)
     if gelu_aux is not None:
         dx = gemm(dy2, weight, b_mn=True, aux=_flat2d(gelu_aux), epi=EPI_GELU_BWD)
+    elif on_gpu(dy2) and weight.shape[0] >= 8192 and _splitk_factor(dy2.shape[0], weight.shape[1], weight.shape[0]) > 1:
+        dx = gemm_splitk(dy2, weight, _splitk_factor(dy2.shape[0], weight.shape[1], weight.shape[0]))
     else:
         dx = gemm(dy2, weight, b_mn=True)
     return dx.view(*grad_output.shape[:-1], weight.shape[1])
