@@ -230,3 +230,18 @@ def test_splitk_lm_head_input_grad():
     ref = dy.float() @ w.float()
     rel = (got.float() - ref).norm() / ref.norm()
     assert rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
+@pytest.mark.parametrize("cfg", [0, 1, 2])
+def test_gemm_cluster_multicast(cluster, a_mn, b_mn, cfg):
+    """B tile fetched once per cluster of M-tiles and TMA-multicast into all of them."""
+    M, N, K = 1024, 1536, 832
+    torch.manual_seed(cluster)
+    a = _rand(K, M) if a_mn else _rand(M, K)
+    b = _rand(K, N) if b_mn else _rand(N, K)
+    ref = _ref_gemm(a, b, a_mn, b_mn)
+    got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, config=cfg, cluster=cluster)
+    rel = (got.float() - ref).norm() / ref.norm()
+    assert rel < 5e-3, rel

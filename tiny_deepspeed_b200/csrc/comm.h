@@ -8,7 +8,7 @@
 namespace tds {
 
 constexpr int kMaxRanks = 8;
-constexpr int kCommMaxBlocks = 64;
+constexpr int kCommMaxBlocks = 128;
 
 // One symmetric allocation as seen from this process: the same buffer on every rank, peer-mapped, plus (when the
 // fabric supports it) one multicast address that aliases all of them (NVLS).
@@ -31,6 +31,9 @@ void reduce_to(const CommCtx& c, const SymmBuf& buf, int64_t elem_off, int64_t n
 // replicate rank src's buf[off, off+numel) into every rank
 void broadcast_from(const CommCtx& c, const SymmBuf& buf, int64_t byte_off, int64_t nbytes, int src, int blocks,
                     int channel, cudaStream_t s);
+// rank src pushes nbytes from its LOCAL pointer into dst[dst_byte_off ...) on every rank (ZeRO-3 parameter fetch)
+void push_from(const CommCtx& c, const void* src_local, const SymmBuf& dst, int64_t dst_byte_off, int64_t nbytes,
+               int src_rank, int blocks, int channel, cudaStream_t s);
 // cross-GPU barrier (all blocks of all ranks)
 void barrier(const CommCtx& c, int channel, cudaStream_t s);
 
@@ -48,6 +51,6 @@ struct OwnedRanges {
 void zero_fused_adam(const CommCtx& c, const SymmBuf& grads, const SymmBuf& params, const OwnedRanges& r, float* master,
                      float* exp_avg, float* exp_avg_sq, const AdamHyper& h, bool bcast_params, int channel,
                      cudaStream_t s);
-constexpr int kZeroChunk = 256 * 8 * 2;   // elements per CTA-iteration in zero_fused_adam
+constexpr int kZeroChunk = 256 * 8 * 4;   // elements per CTA-iteration in zero_fused_adam
 
 }  // namespace tds

@@ -55,6 +55,12 @@ void py_broadcast(const PyComm& c, const PyBuf& b, int64_t byte_off, int64_t nby
   broadcast_from(c.ctx, b.buf, byte_off, nbytes, (int)src, (int)blocks, (int)channel, cur_stream());
   check_launch("broadcast");
 }
+void py_push(const PyComm& c, int64_t src_ptr, const PyBuf& dst, int64_t dst_byte_off, int64_t nbytes, int64_t src_rank,
+             int64_t blocks, int64_t channel) {
+  push_from(c.ctx, reinterpret_cast<const void*>(src_ptr), dst.buf, dst_byte_off, nbytes, (int)src_rank, (int)blocks,
+            (int)channel, cur_stream());
+  check_launch("push");
+}
 void py_barrier(const PyComm& c, int64_t channel) {
   barrier(c.ctx, (int)channel, cur_stream());
   check_launch("barrier");
@@ -107,6 +113,7 @@ void bind_comm(pybind11::module_& m) {
   m.def("comm_reduce_to", &py_reduce_to);
   m.def("comm_broadcast", &py_broadcast);
   m.def("comm_barrier", &py_barrier);
+  m.def("comm_push", &py_push);
   m.def("comm_zero_fused_adam", &py_zero_fused_adam);
   m.attr("COMM_MAX_BLOCKS") = kCommMaxBlocks;
   m.attr("COMM_MAX_RANKS") = kMaxRanks;

@@ -128,13 +128,30 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(const __grid_co
   block_barrier(c, channel);                        // every rank's contribution is in place
   const long long per = (nvec + c.world - 1) / c.world;
   const long long v0 = per * c.rank, v1 = (v0 + per < nvec) ? v0 + per : nvec;
-  for (long long i = v0 + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v1; i += (long long)gridDim.x * blockDim.x) {
-    float f[8];
-    reduce_vec<F32>(c, b, (size_t)(boff + i * 16), f);
-    uint4 o;
-    if (F32) { o.x = __float_as_uint(f[0] * scale); o.y = __float_as_uint(f[1] * scale); o.z = __float_as_uint(f[2] * scale); o.w = __float_as_uint(f[3] * scale); }
-    else { for (int j = 0; j < 8; ++j) f[j] *= scale; o = pack_bf16x8(f); }
-    bcast_vec(c, b, (size_t)(boff + i * 16), o);
+  // NVLink round trips are ~3 us: keep U independent 16-byte requests in flight per thread (Little's law:
+  // blocks x threads x U x 16 B must cover ~770 GB/s x latency ~ 2.3 MB)
+  constexpr int U = 8;
+  const long long stride = (long long)gridDim.x * blockDim.x * U;
+  for (long long base = v0 + (long long)blockIdx.x * blockDim.x * U + threadIdx.x; base < v1; base += stride) {
+    if (b.mc && !F32 && scale == 1.f) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const long long i = base + (long long)u * blockDim.x; if (i < v1) v[u] = mm_ld_reduce_bf16((const char*)b.mc + boff + i * 16); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const long long i = base + (long long)u * blockDim.x; if (i < v1) mm_st((char*)b.mc + boff + i * 16, v[u]); }
+    } else {
+#pragma unroll 2
+      for (int u = 0; u < U; ++u) {
+        const long long i = base + (long long)u * blockDim.x;
+        if (i >= v1) break;
+        float f[8];
+        reduce_vec<F32>(c, b, (size_t)(boff + i * 16), f);
+        uint4 o;
+        if (F32) { o.x = __float_as_uint(f[0] * scale); o.y = __float_as_uint(f[1] * scale); o.z = __float_as_uint(f[2] * scale); o.w = __float_as_uint(f[3] * scale); }
+        else { for (int j = 0; j < 8; ++j) f[j] *= scale; o = pack_bf16x8(f); }
+        bcast_vec(c, b, (size_t)(boff + i * 16), o);
+      }
+    }
   }
   __threadfence_system();
   block_barrier(c, channel);                        // results visible everywhere before anyone returns
@@ -203,6 +220,38 @@ void broadcast_from(const CommCtx& c, const SymmBuf& buf, int64_t byte_off, int6
   broadcast_kernel<<<blocks, kCommThreads, 0, s>>>(c, buf, (long long)byte_off, (long long)((nbytes + 15) / 16), src, channel);
 }
 
+// Owner-push of a tensor into a symmetric staging slot on EVERY rank (ZeRO-3 parameter fetch): the owner streams its
+// local copy through `multimem.st` (the switch replicates: owner egress = 1x the tensor, whatever the world size) or,
+// without multicast, through per-peer stores.  Consumers only take part in the two barriers.
+__global__ void __launch_bounds__(kCommThreads) push_kernel(const __grid_constant__ CommCtx c, const char* __restrict__ src,
+                                                           const __grid_constant__ SymmBuf dst, long long dst_boff,
+                                                           long long nvec, int src_rank, int channel) {
+  block_barrier(c, channel);   // every rank has released the slot's previous contents
+  if (c.rank == src_rank) {
+    constexpr int U = 4;
+    const long long stride = (long long)gridDim.x * blockDim.x * U;
+    for (long long base = (long long)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
+      uint4 v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) { const long long i = base + (long long)u * blockDim.x; if (i < nvec) v[u] = *reinterpret_cast<const uint4*>(src + i * 16); }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = base + (long long)u * blockDim.x;
+        if (i < nvec) bcast_vec(c, dst, (size_t)(dst_boff + i * 16), v[u]);
+      }
+    }
+  }
+  __threadfence_system();
+  block_barrier(c, channel);   // slot contents visible on every rank
+}
+
+void push_from(const CommCtx& c, const void* src_local, const SymmBuf& dst, int64_t dst_byte_off, int64_t nbytes,
+               int src_rank, int blocks, int channel, cudaStream_t s) {
+  if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
+  push_kernel<<<blocks, kCommThreads, 0, s>>>(c, (const char*)src_local, dst, (long long)dst_byte_off,
+                                             (long long)((nbytes + 15) / 16), src_rank, channel);
+}
+
 __global__ void barrier_kernel(const __grid_constant__ CommCtx c, int channel) { block_barrier(c, channel); }
 void barrier(const CommCtx& c, int channel, cudaStream_t s) { barrier_kernel<<<1, 32, 0, s>>>(c, channel); }
 
@@ -241,40 +290,61 @@ __global__ void __launch_bounds__(256) zero_fused_adam_kernel(const __grid_const
     const long long base = (long long)(wb - R.blk_start[t]) * kZeroChunk;
     const long long n = R.numel[t];
     const long long end = base + kZeroChunk < n ? base + kZeroChunk : n;
-    for (long long i = base + threadIdx.x * 8; i < end; i += 256 * 8) {
-      const size_t boff = (size_t)(R.elem_off[t] + i) * 2;
-      float g[8];
-      reduce_vec<false>(c, grads, boff, g);
-      const long long so = R.state_off[t] + i;
-      float w[8], m[8], v[8];
-      *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(master + so);
-      *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(master + so + 4);
-      *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(exp_avg + so);
-      *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(exp_avg + so + 4);
-      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(exp_avg_sq + so);
-      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(exp_avg_sq + so + 4);
+    constexpr int U = 4;               // gradient fetches in flight per thread (NVLink latency hiding)
+    for (long long i0 = base + threadIdx.x * 8; i0 < end; i0 += 256 * 8 * U) {
+      uint4 graw[U];
+      float gsum[U][8];
+      if (grads.mc) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float gg = g[j] * h.grad_scale;
-        if (h.maximize) gg = -gg;
-        if (h.weight_decay != 0.f) {
-          if (h.decoupled) w[j] *= (1.f - h.lr * h.weight_decay);
-          else gg += h.weight_decay * w[j];
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + (long long)u * 256 * 8;
+          if (i < end) graw[u] = mm_ld_reduce_bf16((const char*)grads.mc + (size_t)(R.elem_off[t] + i) * 2);
         }
-        m[j] = h.beta1 * m[j] + (1.f - h.beta1) * gg;
-        v[j] = h.beta2 * v[j] + (1.f - h.beta2) * gg * gg;
-        w[j] -= (h.lr / bc1) * (m[j] / (sqrtf(v[j]) * bc2r + h.eps));
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const long long i = i0 + (long long)u * 256 * 8;
+          if (i < end) reduce_vec<false>(c, grads, (size_t)(R.elem_off[t] + i) * 2, gsum[u]);
+        }
       }
-      *reinterpret_cast<float4*>(master + so) = *reinterpret_cast<float4*>(w);
-      *reinterpret_cast<float4*>(master + so + 4) = *reinterpret_cast<float4*>(w + 4);
-      *reinterpret_cast<float4*>(exp_avg + so) = *reinterpret_cast<float4*>(m);
-      *reinterpret_cast<float4*>(exp_avg + so + 4) = *reinterpret_cast<float4*>(m + 4);
-      *reinterpret_cast<float4*>(exp_avg_sq + so) = *reinterpret_cast<float4*>(v);
-      *reinterpret_cast<float4*>(exp_avg_sq + so + 4) = *reinterpret_cast<float4*>(v + 4);
-      const uint4 o = pack_bf16x8(w);
-      const size_t poff = (size_t)(R.pelem_off[t] + i) * 2;
-      if (bcast) bcast_vec(c, params, poff, o);
-      else *reinterpret_cast<uint4*>(local_param + poff) = o;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + (long long)u * 256 * 8;
+        if (i >= end) break;
+        float g[8];
+        if (grads.mc) { for (int j = 0; j < 8; ++j) g[j] = 0.f; acc_bf16x8(g, graw[u]); }
+        else { for (int j = 0; j < 8; ++j) g[j] = gsum[u][j]; }
+        const long long so = R.state_off[t] + i;
+        float w[8], m[8], v[8];
+        *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(master + so);
+        *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(master + so + 4);
+        *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(exp_avg + so);
+        *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(exp_avg + so + 4);
+        *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(exp_avg_sq + so);
+        *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(exp_avg_sq + so + 4);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float gg = g[j] * h.grad_scale;
+          if (h.maximize) gg = -gg;
+          if (h.weight_decay != 0.f) {
+            if (h.decoupled) w[j] *= (1.f - h.lr * h.weight_decay);
+            else gg += h.weight_decay * w[j];
+          }
+          m[j] = h.beta1 * m[j] + (1.f - h.beta1) * gg;
+          v[j] = h.beta2 * v[j] + (1.f - h.beta2) * gg * gg;
+          w[j] -= (h.lr / bc1) * (m[j] / (sqrtf(v[j]) * bc2r + h.eps));
+        }
+        *reinterpret_cast<float4*>(master + so) = *reinterpret_cast<float4*>(w);
+        *reinterpret_cast<float4*>(master + so + 4) = *reinterpret_cast<float4*>(w + 4);
+        *reinterpret_cast<float4*>(exp_avg + so) = *reinterpret_cast<float4*>(m);
+        *reinterpret_cast<float4*>(exp_avg + so + 4) = *reinterpret_cast<float4*>(m + 4);
+        *reinterpret_cast<float4*>(exp_avg_sq + so) = *reinterpret_cast<float4*>(v);
+        *reinterpret_cast<float4*>(exp_avg_sq + so + 4) = *reinterpret_cast<float4*>(v + 4);
+        const uint4 o = pack_bf16x8(w);
+        const size_t poff = (size_t)(R.pelem_off[t] + i) * 2;
+        if (bcast) bcast_vec(c, params, poff, o);
+        else *reinterpret_cast<uint4*>(local_param + poff) = o;
+      }
     }
   }
   __threadfence_system();

@@ -45,6 +45,7 @@ struct GemmDev {
   int M, N, K, batch, nb2;
   int a_mn, b_mn;
   int tri;
+  int cm;         // cluster size along M (1, 2, 4, 8): B tile fetched once per cluster and multicast
   int tma_store;  // epilogue goes registers -> swizzled smem -> TMA store (bf16 out, no accumulate, aligned)
   int dbg;      // TDS_GEMM_DBG bits (profiling only): 1 = no global stores, 2 = no MMA issue, 4 = no epilogue body
   uint32_t idesc;
@@ -92,7 +93,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
     if (g.tma_store) ptx::prefetch_tmap(&tma_d);
-    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), 1); }
+    // a smem stage is refilled by EVERY CTA of the cluster (B slices are multicast), so it is free only when all
+    // cm MMA issuers have released it
+    for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (uint32_t)g.cm); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
     ptx::fence_mbar_init();
   }
@@ -104,6 +107,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t cta_rank = g.cm > 1 ? ptx::cluster_ctarank() : 0u;
+  const uint16_t cta_mask = (uint16_t)((1u << g.cm) - 1u);
+  if (g.cm > 1) ptx::cluster_sync();   // peers' barriers exist before any multicast / remote commit targets them
 
   const int m_tiles = (g.M + BM - 1) / BM;
   const int n_tiles = (g.N + BN - 1) / BN;
@@ -133,12 +139,28 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int i = 0; i < BM / 64; ++i)
               ptx::tma_load_4d(a_dst + i * (BK * 128), &tma_a, full_bar(stage), m0 + 64 * i, k0, b2, b1);
           }
-          if (!g.b_mn) {
-            ptx::tma_load_4d(b_dst, &tma_b, full_bar(stage), k0, n0, b2, b1);
-          } else {
+          if (g.cm == 1) {
+            if (!g.b_mn) {
+              ptx::tma_load_4d(b_dst, &tma_b, full_bar(stage), k0, n0, b2, b1);
+            } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i)
-              ptx::tma_load_4d(b_dst + i * (BK * 128), &tma_b, full_bar(stage), n0 + 64 * i, k0, b2, b1);
+              for (int i = 0; i < BN / 64; ++i)
+                ptx::tma_load_4d(b_dst + i * (BK * 128), &tma_b, full_bar(stage), n0 + 64 * i, k0, b2, b1);
+            }
+          } else {
+            // The cm CTAs of the cluster work on cm consecutive M tiles of the SAME N tile: each fetches 1/cm of
+            // the B tile and the TMA multicasts it into every CTA's smem (one L2 / NVLink read per cluster).
+            if (!g.b_mn) {
+              const uint32_t rows = BN / g.cm;
+              ptx::tma_load_4d_mc(b_dst + cta_rank * rows * 128u, &tma_b, full_bar(stage), k0, n0 + (int)(cta_rank * rows),
+                                  b2, b1, cta_mask);
+            } else {
+              const uint32_t krows = BK / g.cm;
+#pragma unroll
+              for (int i = 0; i < BN / 64; ++i)
+                ptx::tma_load_4d_mc(b_dst + i * (BK * 128) + cta_rank * krows * 128u, &tma_b, full_bar(stage),
+                                    n0 + 64 * i, k0 + (int)(cta_rank * krows), b2, b1, cta_mask);
+            }
           }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
@@ -174,7 +196,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint64_t db = ptx::make_smem_desc(b_s + k * b_adv, b_lbo, 1024);
             if (!(g.dbg & 2)) ptx::mma_f16_ss(d_tmem, da, db, g.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          ptx::mma_commit(empty_bar(stage));                 // smem stage reusable once these MMAs retire
+          // smem stage reusable once these MMAs retire (told to every CTA of the cluster when B is multicast)
+          if (g.cm == 1) ptx::mma_commit(empty_bar(stage));
+          else ptx::mma_commit_mc(empty_bar(stage), cta_mask);
           if (kb == kb1 - 1) ptx::mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
         }
         __syncwarp();
@@ -360,6 +384,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (g.cm > 1) ptx::cluster_sync();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, C::kTmemCols);
@@ -387,13 +412,14 @@ static EncodeTiledFn get_encode() {
 }
 
 // 4-D map over one bf16 operand: dims (inner, rows, nb2, nb1)
-static bool make_map(CUtensorMap* out, const GemmOperand& op, int rows_mn, int K, int nb1, int nb2, int box_rows_kmajor) {
+static bool make_map(CUtensorMap* out, const GemmOperand& op, int rows_mn, int K, int nb1, int nb2, int box_rows_kmajor,
+                     int box_krows_mnmajor = BK) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[4];
   cuuint32_t box[4];
   if (!op.mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows_mn; box[0] = BK; box[1] = (cuuint32_t)box_rows_kmajor; }
-  else              { dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = BK; }
+  else              { dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = (cuuint32_t)box_krows_mnmajor; }
   dims[2] = (cuuint64_t)nb2; dims[3] = (cuuint64_t)nb1;
   box[2] = 1; box[3] = 1;
   const cuuint64_t row_bytes = (cuuint64_t)op.ld * 2;
@@ -431,6 +457,24 @@ static int pick_config(const GemmParams& p) {
 }
 
 template <int BN>
+static int max_clusters(int cm) {
+  static int cache[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (cache[cm]) return cache[cm];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(g_num_sms / cm * cm);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<BN>::kSmem;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cm; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
+  cache[cm] = n;
+  return n;
+}
+
+template <int BN>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                    const GemmDev& g, int tiles, cudaStream_t s) {
   static bool attr_done = false;
@@ -438,8 +482,38 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
     cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
     attr_done = true;
   }
-  const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-  gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, s>>>(ta, tb, td, tx, g);
+  if (g.cm == 1) {
+    const int grid = tiles < g_num_sms ? tiles : g_num_sms;
+    gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, s>>>(ta, tb, td, tx, g);
+    return;
+  }
+  // cluster launch: cm consecutive CTAs = cm consecutive M tiles of one N tile; grid is a whole number of clusters
+  int clusters = tiles / g.cm;
+  const int cap = max_clusters<BN>(g.cm);
+  if (clusters > cap) clusters = cap;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(clusters * g.cm);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = Cfg<BN>::kSmem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = g.cm; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, gemm_kernel<BN>, ta, tb, td, tx, g);
+}
+
+// cluster size along M: B-tile multicast divides L2->SM (or NVLink, for a ZeRO-3 peer weight) operand traffic by cm
+static int pick_cluster(const GemmParams& p, int bn) {
+  static const int env = getenv("TDS_GEMM_CM") ? atoi(getenv("TDS_GEMM_CM")) : -1;
+  // measured on B200 (profiles/r1_gemm_cluster_sweep.md): at M = 1024 the GPT-2 GEMMs are latency-, not L2-bound, and
+  // cluster launch costs more than the multicast saves -> off unless requested
+  int want = p.cluster_m > 0 ? p.cluster_m : (env >= 0 ? env : 1);
+  if (want <= 1 || p.tri != 0 || p.batch != 1) return 1;
+  const int m_tiles = (p.M + BM - 1) / BM;
+  int cm = 8;
+  while (cm > 1 && (cm > want || m_tiles % cm != 0 || (bn / cm) % 8 != 0)) cm >>= 1;
+  return cm;
 }
 
 void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
@@ -454,7 +528,8 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   const int nb2 = p.nbatch2 > 0 ? p.nbatch2 : 1;
   const int nb1 = p.batch / nb2;
   CUtensorMap ta, tb;
-  if (!make_map(&ta, p.a, p.M, p.K, nb1, nb2, BM) || !make_map(&tb, p.b, p.N, p.K, nb1, nb2, bn)) {
+  const int cm = pick_cluster(p, bn);
+  if (!make_map(&ta, p.a, p.M, p.K, nb1, nb2, BM) || !make_map(&tb, p.b, p.N, p.K, nb1, nb2, bn / cm, BK / cm)) {
     fprintf(stderr, "[tds] gemm: tensor map creation failed (M=%d N=%d K=%d)\n", p.M, p.N, p.K);
     abort();
   }
@@ -468,6 +543,7 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   static const int dbg_env = getenv("TDS_GEMM_DBG") ? atoi(getenv("TDS_GEMM_DBG")) : 0;
   g.dbg = dbg_env;
   g.idesc = make_idesc_bf16(BM, bn, p.a.mn_major, p.b.mn_major);
+  g.cm = cm;
   const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.batch;
   // output through TMA (coalesced 128-byte rows) whenever the layout allows it
   CUtensorMap td = ta, tx = ta;

@@ -26,6 +26,7 @@ struct GemmParams {
   float alpha;
   int M, N, K, batch, nbatch2;
   int config;             // tile configuration index, -1 = heuristic
+  int cluster_m;          // requested cluster size along M for B-tile multicast (0 = default, 1 = off)
   int tri;                // causal structure: 0 none, 1 skip tiles above the diagonal (S, dP),
                           // 2 K-range ends at the tile's last row (P.V, dS.K), 3 K-range starts at the tile's first row (P^T.dY, dS^T.Q)
 };

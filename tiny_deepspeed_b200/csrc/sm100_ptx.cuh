@@ -56,6 +56,24 @@ TDS_PTX void tma_load_4d(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, 
       : "memory");
 }
 
+// multicast variant: the box lands at the same smem offset of every CTA in `cta_mask`, each CTA's mbarrier (same offset)
+// receives the complete_tx bytes
+TDS_PTX void tma_load_4d_mc(uint32_t dst_smem, const CUtensorMap* m, uint32_t bar, int c0, int c1, int c2, int c3,
+                            uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;"
+      ::"r"(dst_smem), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+
+// ---- thread-block clusters ---------------------------------------------------------------------------------
+TDS_PTX uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+TDS_PTX void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 TDS_PTX void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
@@ -92,6 +110,12 @@ TDS_PTX void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint3
 // All previously issued tcgen05.mma of this thread arrive on the mbarrier when they complete.
 TDS_PTX void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// ... and on the same barrier of every CTA in `cta_mask` (stage release when the operand tile was multicast)
+TDS_PTX void mma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
 // 32 lanes x 32 consecutive fp32 columns: thread i of the warp receives row (lane base + i), columns [c, c+32)

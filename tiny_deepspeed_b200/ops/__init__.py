@@ -65,7 +65,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
          bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
          epi: int = EPI_NONE, accumulate: bool = False, alpha: float = 1.0,
-         config: Optional[int] = None, tri: int = 0) -> torch.Tensor:
+         config: Optional[int] = None, tri: int = 0, cluster: int = 0) -> torch.Tensor:
     """General (optionally batched) GEMM ``D[m,n] = alpha * sum_k A(m,k) * B(n,k)`` (+epilogue).
 
     ``a`` is stored ``[.., M, K]`` (K-major) or, with ``a_mn=True``, ``[.., K, M]`` (MN-major);
@@ -74,7 +74,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     On CUDA this is one launch of the persistent tcgen05 kernel (csrc/gemm_sm100.cu).
     """
     if on_gpu(a, b):
-        return _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alpha, config, tri)
+        return _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alpha, config, tri, cluster)
     A = a.transpose(-1, -2) if a_mn else a
     Bm = b.transpose(-1, -2) if b_mn else b
     acc = torch.matmul(A.float(), Bm.float().transpose(-1, -2)) * alpha
@@ -97,7 +97,11 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
-def _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alpha, config, tri=0):
+def _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alpha, config, tri=0, cluster=0):
+    if getattr(b, "_tds_remote", False):
+        # B aliases a peer GPU's memory (ZeRO-3 direct-fetch mode).  TMA *multicast* sourced from peer-mapped memory
+        # wedged the GPU in testing (2xB200, r1), so the peer-fetch GEMM always runs with plain per-CTA TMA loads.
+        cluster = 1
     if a.dim() == 2:
         M = a.shape[1] if a_mn else a.shape[0]
         N = b.shape[1] if b_mn else b.shape[0]
@@ -109,7 +113,7 @@ def _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alp
     if out is None:
         out = torch.empty(shape, device=a.device, dtype=out_dtype or a.dtype)
     ext().gemm(a, b, out, a_mn, b_mn, bias, aux, int(epi), bool(accumulate), float(alpha),
-               -1 if config is None else int(config), int(tri))
+               -1 if config is None else int(config), int(tri), int(cluster))
     count_launch()
     return out
 

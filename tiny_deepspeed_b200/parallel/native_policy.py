@@ -115,6 +115,14 @@ class NativePolicy(CommPolicy):
         if cur:
             self.buckets.append(cur)
         self.bucket_of = {n: i for i, b in enumerate(self.buckets) for n in b}
+        # ---- ZeRO-3 parameter fetch ----------------------------------------------------------------------------
+        import os
+        self.fetch = os.environ.get("TDS_ZERO3_FETCH", "push")     # "push": owner multicast + prefetch; "peer": GEMM pulls
+        self.lookahead, self.nslots = 2, 4
+        self._seq, self._seq_frozen, self._pos, self._fetched = [], False, 0, {}
+        if mode == "zero3" and self.fetch == "push" and self.world > 1:
+            self.slot_bytes = (max(_pad(v) for v in self.numel.values()) * 2 + 4095) // 4096 * 4096
+            self.S = symm.alloc(self.nslots * self.slot_bytes, self.device, group)
         self._reset_round()
         self._accumulated = set()      # names holding un-synced micro-batch gradients
         self._opt_state = None
@@ -190,6 +198,7 @@ class NativePolicy(CommPolicy):
                                     blocks=self.comm_blocks, channel=0)
             self._accumulated.clear()
             self._reset_round()
+            self._end_round_zero3()
 
     # ------------------------------------------------------------------------------------------ ZeRO-3 parameters
     def acquire(self, param, *, backward=False):
@@ -197,10 +206,60 @@ class NativePolicy(CommPolicy):
             return param
         n = self._name_of[id(param)]
         owner = self._owner(n)
+        if self.fetch == "peer":
+            if owner == self.rank:
+                return param.data
+            # alias of the OWNER's memory (NVLink peer mapping): the consuming GEMM's TMA producer pulls the weight
+            # tile by tile straight into shared memory (all-gather fused into the GEMM; M/128 x NVLink re-reads)
+            t = self.P.peer(owner, self.shape[n], self.dtype, self.poff[n] * 2)
+            t._tds_remote = True
+            return t
+        # ---- owner-push mode: the owner multicasts the tensor into a staging slot of every rank, up to
+        # `lookahead` uses ahead of the consumer, on the communication stream -----------------------------------
+        pos = self._pos
+        self._pos += 1
+        if self._seq_frozen and (pos >= len(self._seq) or self._seq[pos] != n):
+            self._seq_frozen, self._seq, pos = False, [], 0       # use order changed: re-record from here
+            self._pos = 1
+            self._fetched.clear()
+        if not self._seq_frozen:
+            self._seq.append(n)
+        if pos not in self._fetched:
+            self._launch_fetch(pos)
+        if self._seq_frozen:
+            for la in range(1, self.lookahead + 1):
+                if pos + la < len(self._seq) and (pos + la) not in self._fetched:
+                    self._launch_fetch(pos + la)
+        torch.cuda.current_stream(self.device).wait_event(self._fetched[pos])
         if owner == self.rank:
             return param.data
-        # alias of the OWNER's memory (NVLink peer mapping): the consuming kernel pulls it tile by tile
-        return self.P.peer(owner, self.shape[n], self.dtype, self.poff[n] * 2)
+        slot = pos % self.nslots
+        nbytes = self.numel[n] * 2
+        return self.S.local[slot * self.slot_bytes: slot * self.slot_bytes + nbytes].view(self.dtype).view(self.shape[n])
+
+    def _launch_fetch(self, pos):
+        n = self._seq[pos]
+        owner = self._owner(n)
+        slot = pos % self.nslots
+        src = self.params[n].data_ptr() if owner == self.rank else 0
+        # everything enqueued so far on the compute stream precedes the push: the slot's previous reader and the
+        # optimizer update of the source tensor are therefore complete when the owner starts writing
+        self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(self.comm_stream):
+            ops.ext().comm_push(self.comm.ctx, int(src), self.S.buf, slot * self.slot_bytes, _pad(self.numel[n]) * 2,
+                                owner, self.comm_blocks, 2)
+            ops.count_launch()
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+        self._fetched[pos] = ev
+        self.stats["bytes"] += self.numel[n] * 2
+
+    def _end_round_zero3(self):
+        if self.mode == "zero3" and self.fetch == "push":
+            if not self._seq_frozen and self._seq:
+                self._seq_frozen = True
+            self._pos = 0
+            self._fetched.clear()
 
     def release(self, param, full):
         return
@@ -255,4 +314,5 @@ class NativePolicy(CommPolicy):
             p.grad = None
         self._accumulated.clear()
         self._reset_round()
+        self._end_round_zero3()
         return True
