@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--backend", default="auto", choices=["auto", "native", "dist"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--partition", default="greedy")
+    ap.add_argument("--partition", default="balanced", choices=["greedy", "contiguous", "balanced"])
     return ap.parse_args()
 
 
