@@ -60,3 +60,22 @@ def test_training_decreases_loss_and_graph_matches_eager():
 def test_smoke_entry():
     import __graft_entry__ as g
     g.smoke()
+
+
+def test_optimizer_in_backward_overlap_matches_plain_step():
+    cfg, m1 = _mk(2)
+    m2 = copy.deepcopy(m1)
+    x = torch.randint(0, cfg.vocab_size, (2, 256), device="cuda")
+    y = torch.randint(0, cfg.vocab_size, (2, 256), device="cuda")
+    o1 = tds.AdamW(m1.named_parameters(), lr=1e-3, weight_decay=0.1)
+    o2 = tds.AdamW(m2.named_parameters(), lr=1e-3, weight_decay=0.1)
+    s1 = tds.TrainStep(m1, o1, use_graph=False, overlap_step=False)
+    s2 = tds.TrainStep(m2, o2, use_graph=False, overlap_step=True)
+    s2.overlap.bucket_bytes = 64 << 10          # several buckets even for the tiny model
+    l1 = [float(s1(x, y)) for _ in range(6)]
+    l2 = [float(s2(x, y)) for _ in range(6)]
+    assert s2.overlap.stats["overlapped_buckets"] > 0
+    assert o1.step_count == o2.step_count == 6
+    assert l2 == pytest.approx(l1, rel=1e-4, abs=1e-4), (l1, l2)
+    for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
+        torch.testing.assert_close(a.float(), b.float(), rtol=1e-3, atol=1e-4, msg=n)

@@ -7,7 +7,36 @@
 
 #define TDS_DEVICE __device__ __forceinline__
 
+#include <stdlib.h>
+#include <utility>
+
 namespace tds {
+
+// ---- Programmatic Dependent Launch ------------------------------------------------------------------------------
+// Every kernel of ours begins with pdl_launch(); pdl_wait(): the NEXT kernel's CTAs may be scheduled (and run their
+// prologue up to their own pdl_wait) while this grid is still draining, which hides launch latency between the ~330
+// short kernels of a training step.  griddepcontrol.wait returns only when the prerequisite grid has fully completed
+// and its writes are visible, so data hazards are exactly those of plain stream order.
+TDS_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+TDS_DEVICE void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  // measured (profiles/r1_pdl.md): inside the CUDA graph the step is 4.87 ms without and 4.98 ms with PDL edges, so
+  // the attribute is opt-in (TDS_PDL=1); the griddepcontrol instructions are no-ops without it
+  static const bool on = getenv("TDS_PDL") && atoi(getenv("TDS_PDL")) != 0;
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
 
 constexpr int kWarp = 32;
 

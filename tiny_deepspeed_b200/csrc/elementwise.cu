@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const T* __restri
                                                               const T* __restrict__ b, T* __restrict__ y,
                                                               float* __restrict__ mean, float* __restrict__ rstd,
                                                               int M, int N, float eps) {
+  pdl_launch(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * kLnWarps + (threadIdx.x >> 5);
   if (row >= M) return;
@@ -81,7 +82,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_fwd_kernel(const T* __restri
 void layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd, int M, int N,
                    float eps, int dtype, cudaStream_t s) {
   dim3 grid((M + kLnWarps - 1) / kLnWarps), block(kLnWarps * 32);
-  TDS_DISPATCH(dtype, (ln_fwd_kernel<T><<<grid, block, 0, s>>>((const T*)x, (const T*)w, (const T*)b, (T*)y, mean,
+  TDS_DISPATCH(dtype, (launch_k(ln_fwd_kernel<T>, dim3(grid), dim3(block), 0, s, (const T*)x, (const T*)w, (const T*)b, (T*)y, mean,
                                                                 rstd, M, N, eps)));
 }
 
@@ -97,6 +98,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const T* __restri
                                                               const float* __restrict__ rstd, const T* __restrict__ add,
                                                               T* __restrict__ dx, float* __restrict__ scratch, int M,
                                                               int N) {
+  pdl_launch(); pdl_wait();
   extern __shared__ float sm[];  // [kLnWarps][2][N]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float* sdw = sm + (size_t)wid * 2 * N;
@@ -163,6 +165,7 @@ __global__ void __launch_bounds__(kLnWarps * 32) ln_bwd_kernel(const T* __restri
 template <typename T>
 __global__ void ln_bwd_reduce_kernel(const float* __restrict__ scratch, T* __restrict__ dw, T* __restrict__ db, int P,
                                      int N, int accumulate) {
+  pdl_launch(); pdl_wait();
   // one warp per 32 columns x {dw,db}; lanes own a column, loop over the P partial rows (coalesced)
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= 2 * N) return;
@@ -181,9 +184,9 @@ void layernorm_bwd_generic(const void* dy, const void* x, const void* w, const f
   TDS_DISPATCH(dtype, {
     if (smem > 48 * 1024)
       cudaFuncSetAttribute(ln_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    ln_bwd_kernel<T><<<ctas, kLnWarps * 32, smem, s>>>((const T*)dy, (const T*)x, (const T*)w, mean, rstd,
+    launch_k(ln_bwd_kernel<T>, dim3(ctas), dim3(kLnWarps * 32), smem, s, (const T*)dy, (const T*)x, (const T*)w, mean, rstd,
                                                         (const T*)add, (T*)dx, scratch, M, N);
-    ln_bwd_reduce_kernel<T><<<(2 * N + 127) / 128, 128, 0, s>>>(scratch, (T*)dw, (T*)db, ctas, N, accumulate ? 1 : 0);
+    launch_k(ln_bwd_reduce_kernel<T>, dim3((2 * N + 127) / 128), dim3(128), 0, s, scratch, (T*)dw, (T*)db, ctas, N, accumulate ? 1 : 0);
   });
 }
 
@@ -193,6 +196,7 @@ void layernorm_bwd_generic(const void* dy, const void* x, const void* w, const f
 template <typename T>
 __global__ void emb_fwd_kernel(const int64_t* __restrict__ idx, const T* __restrict__ weight, const T* __restrict__ add,
                                int add_rows, T* __restrict__ out, int ntok, int dim, int64_t vocab) {
+  pdl_launch(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= ntok) return;
@@ -219,7 +223,7 @@ __global__ void emb_fwd_kernel(const int64_t* __restrict__ idx, const T* __restr
 void embedding_fwd(const int64_t* idx, const void* weight, const void* add, int add_rows, void* out, int ntok, int dim,
                    int64_t vocab, int dtype, cudaStream_t s) {
   const int warps = 4;
-  TDS_DISPATCH(dtype, (emb_fwd_kernel<T><<<(ntok + warps - 1) / warps, warps * 32, 0, s>>>(
+  TDS_DISPATCH(dtype, (launch_k(emb_fwd_kernel<T>, dim3((ntok + warps - 1) / warps), dim3(warps * 32), 0, s, 
                           idx, (const T*)weight, (const T*)add, add_rows > 0 ? add_rows : 1, (T*)out, ntok, dim, vocab)));
 }
 
@@ -234,6 +238,7 @@ TDS_DEVICE void atomic_add2(float* p, float a, float b) {
 template <typename T>
 __global__ void emb_bwd_kernel(const int64_t* __restrict__ idx, const T* __restrict__ dy, T* __restrict__ dw, int ntok,
                                int dim, int64_t vocab, int64_t padding_idx) {
+  pdl_launch(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= ntok) return;
@@ -253,7 +258,7 @@ void embedding_bwd(const int64_t* idx, const void* dy, void* dw, bool accumulate
   const size_t esz = dtype == kBF16 ? 2 : 4;
   if (!accumulate) cudaMemsetAsync(dw, 0, (size_t)vocab * dim * esz, s);
   const int warps = 4;
-  TDS_DISPATCH(dtype, (emb_bwd_kernel<T><<<(ntok + warps - 1) / warps, warps * 32, 0, s>>>(
+  TDS_DISPATCH(dtype, (launch_k(emb_bwd_kernel<T>, dim3((ntok + warps - 1) / warps), dim3(warps * 32), 0, s, 
                           idx, (const T*)dy, (T*)dw, ntok, dim, vocab, padding_idx)));
 }
 
@@ -264,6 +269,7 @@ void embedding_bwd(const int64_t* idx, const void* dy, void* dw, bool accumulate
 // =====================================================================================================
 __global__ void __launch_bounds__(128) softmax_causal_fwd_kernel(__nv_bfloat16* __restrict__ S, int nrows, int T,
                                                                  float scale_log2e) {
+  pdl_launch(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gr = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (gr >= nrows) return;
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(128) softmax_causal_fwd_kernel(__nv_bfloat16* 
 
 void softmax_causal_fwd_generic(void* s_inout, int nmat, int T, float scale, cudaStream_t s) {
   const int nrows = nmat * T;
-  softmax_causal_fwd_kernel<<<(nrows + 3) / 4, 128, 0, s>>>((__nv_bfloat16*)s_inout, nrows, T,
+  launch_k(softmax_causal_fwd_kernel, dim3((nrows + 3) / 4), dim3(128), 0, s, (__nv_bfloat16*)s_inout, nrows, T,
                                                             scale * 1.4426950408889634f);
 }
 
@@ -312,6 +318,7 @@ void softmax_causal_fwd_generic(void* s_inout, int nmat, int T, float scale, cud
 __global__ void __launch_bounds__(128) softmax_causal_bwd_kernel(const __nv_bfloat16* __restrict__ P,
                                                                  __nv_bfloat16* __restrict__ dP, int nrows, int T,
                                                                  float scale) {
+  pdl_launch(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gr = blockIdx.x * 4 + (threadIdx.x >> 5);
   if (gr >= nrows) return;
@@ -346,7 +353,7 @@ __global__ void __launch_bounds__(128) softmax_causal_bwd_kernel(const __nv_bflo
 
 void softmax_causal_bwd_generic(const void* p, void* dp_inout, int nmat, int T, float scale, cudaStream_t s) {
   const int nrows = nmat * T;
-  softmax_causal_bwd_kernel<<<(nrows + 3) / 4, 128, 0, s>>>((const __nv_bfloat16*)p, (__nv_bfloat16*)dp_inout, nrows,
+  launch_k(softmax_causal_bwd_kernel, dim3((nrows + 3) / 4), dim3(128), 0, s, (const __nv_bfloat16*)p, (__nv_bfloat16*)dp_inout, nrows,
                                                             T, scale);
 }
 
@@ -360,6 +367,7 @@ __global__ void __launch_bounds__(kXentThreads) xent_fwd_kernel(const T* __restr
                                                                 const int64_t* __restrict__ tgt,
                                                                 float* __restrict__ row_loss, float* __restrict__ lse,
                                                                 int V) {
+  pdl_launch(); pdl_wait();
   __shared__ float red[32];
   const int row = blockIdx.x;
   const T* l = logits + (size_t)row * V;
@@ -392,6 +400,7 @@ __global__ void __launch_bounds__(kXentThreads) xent_fwd_kernel(const T* __restr
 }
 
 __global__ void mean_kernel(const float* __restrict__ v, float* __restrict__ out, int n) {
+  pdl_launch(); pdl_wait();
   __shared__ float red[32];
   float a = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) a += v[i];
@@ -401,8 +410,8 @@ __global__ void mean_kernel(const float* __restrict__ v, float* __restrict__ out
 
 void xent_fwd(const void* logits, const int64_t* tgt, float* row_loss, float* lse, float* loss, int M, int V, int dtype,
               cudaStream_t s) {
-  TDS_DISPATCH(dtype, (xent_fwd_kernel<T><<<M, kXentThreads, 0, s>>>((const T*)logits, tgt, row_loss, lse, V)));
-  mean_kernel<<<1, 1024, 0, s>>>(row_loss, loss, M);
+  TDS_DISPATCH(dtype, (launch_k(xent_fwd_kernel<T>, dim3(M), dim3(kXentThreads), 0, s, (const T*)logits, tgt, row_loss, lse, V)));
+  launch_k(mean_kernel, dim3(1), dim3(1024), 0, s, row_loss, loss, M);
 }
 
 template <typename T>
@@ -411,6 +420,7 @@ __global__ void __launch_bounds__(kXentThreads) xent_bwd_kernel(const T* __restr
                                                                 const float* __restrict__ lse,
                                                                 const float* __restrict__ gloss, T* __restrict__ dl,
                                                                 int M, int V) {
+  pdl_launch(); pdl_wait();
   const int row = blockIdx.x;
   const T* l = logits + (size_t)row * V;
   T* d = dl + (size_t)row * V;
@@ -431,7 +441,7 @@ __global__ void __launch_bounds__(kXentThreads) xent_bwd_kernel(const T* __restr
 void xent_bwd(const void* logits, const int64_t* tgt, const float* lse, const float* gloss, void* dlogits, int M, int V,
               int dtype, cudaStream_t s) {
   TDS_DISPATCH(dtype,
-               (xent_bwd_kernel<T><<<M, kXentThreads, 0, s>>>((const T*)logits, tgt, lse, gloss, (T*)dlogits, M, V)));
+               (launch_k(xent_bwd_kernel<T>, dim3(M), dim3(kXentThreads), 0, s, (const T*)logits, tgt, lse, gloss, (T*)dlogits, M, V)));
 }
 
 // =====================================================================================================
@@ -439,6 +449,7 @@ void xent_bwd(const void* logits, const int64_t* tgt, const float* lse, const fl
 // =====================================================================================================
 template <typename T, bool BWD>
 __global__ void gelu_kernel(const T* __restrict__ a, const T* __restrict__ x, T* __restrict__ out, int64_t n) {
+  pdl_launch(); pdl_wait();
   const int64_t nvec = n >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float xv[8], av[8];
@@ -458,15 +469,16 @@ static int ew_grid(int64_t n) {
   return (int)(b < 1 ? 1 : (b > 148 * 8 ? 148 * 8 : b));
 }
 void gelu_fwd(const void* x, void* y, int64_t n, int dtype, cudaStream_t s) {
-  TDS_DISPATCH(dtype, (gelu_kernel<T, false><<<ew_grid(n), 256, 0, s>>>(nullptr, (const T*)x, (T*)y, n)));
+  TDS_DISPATCH(dtype, (launch_k(gelu_kernel<T, false>, dim3(ew_grid(n)), dim3(256), 0, s, nullptr, (const T*)x, (T*)y, n)));
 }
 void gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, cudaStream_t s) {
-  TDS_DISPATCH(dtype, (gelu_kernel<T, true><<<ew_grid(n), 256, 0, s>>>((const T*)dy, (const T*)x, (T*)dx, n)));
+  TDS_DISPATCH(dtype, (launch_k(gelu_kernel<T, true>, dim3(ew_grid(n)), dim3(256), 0, s, (const T*)dy, (const T*)x, (T*)dx, n)));
 }
 
 // out[n] (+)= sum_m x[m][n]; CTA = 32 columns x 8 row-lanes, rows strided, then smem fold
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, T* __restrict__ out, int M, int N, int accumulate) {
+  pdl_launch(); pdl_wait();
   __shared__ float sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -484,7 +496,7 @@ __global__ void colsum_kernel(const T* __restrict__ x, T* __restrict__ out, int 
   }
 }
 void colsum(const void* x, void* out, bool accumulate, int M, int N, int dtype, cudaStream_t s) {
-  TDS_DISPATCH(dtype, (colsum_kernel<T><<<(N + 31) / 32, 256, 0, s>>>((const T*)x, (T*)out, M, N, accumulate ? 1 : 0)));
+  TDS_DISPATCH(dtype, (launch_k(colsum_kernel<T>, dim3((N + 31) / 32), dim3(256), 0, s, (const T*)x, (T*)out, M, N, accumulate ? 1 : 0)));
 }
 
 }  // namespace tds

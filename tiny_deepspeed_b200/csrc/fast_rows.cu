@@ -24,6 +24,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_fast_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
     const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ add,
     __nv_bfloat16* __restrict__ dx, float* __restrict__ scratch, int M, int N) {
+  pdl_launch(); pdl_wait();
   extern __shared__ float sm[];   // [kRowWarps][2N]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   float* sdw = sm + (size_t)wid * 2 * N;
@@ -91,6 +92,7 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_fast_kernel(
 
 __global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ scratch, __nv_bfloat16* __restrict__ dw,
                                                      __nv_bfloat16* __restrict__ db, int P, int N, int accumulate) {
+  pdl_launch(); pdl_wait();
   __shared__ float sm[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + tx;
@@ -119,10 +121,10 @@ static void launch_ln_bwd(const void* dy, const void* x, const void* w, const fl
   const size_t smem = (size_t)kRowWarps * 2 * N * sizeof(float);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(ln_bwd_fast_kernel<MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
-  ln_bwd_fast_kernel<MAXV><<<ctas, kRowWarps * 32, smem, s>>>(
+  launch_k(ln_bwd_fast_kernel<MAXV>, dim3(ctas), dim3(kRowWarps * 32), smem, s, 
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, mean, rstd, (const __nv_bfloat16*)add,
       (__nv_bfloat16*)dx, scratch, M, N);
-  ln_fold_kernel<<<(2 * N + 31) / 32, 256, 0, s>>>(scratch, (__nv_bfloat16*)dw, (__nv_bfloat16*)db, ctas, N, accumulate ? 1 : 0);
+  launch_k(ln_fold_kernel, dim3((2 * N + 31) / 32), dim3(256), 0, s, scratch, (__nv_bfloat16*)dw, (__nv_bfloat16*)db, ctas, N, accumulate ? 1 : 0);
 }
 
 void layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, const void* add,
@@ -142,6 +144,7 @@ void layernorm_bwd(const void* dy, const void* x, const void* w, const float* me
 template <int MAXV>
 __global__ void __launch_bounds__(256) softmax_fwd_fast_kernel(__nv_bfloat16* __restrict__ S, int nrows, int T,
                                                               float scale_log2e) {
+  pdl_launch(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gr = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (gr >= nrows) return;
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(256) softmax_fwd_fast_kernel(__nv_bfloat16* __
 template <int MAXV>
 __global__ void __launch_bounds__(256) softmax_bwd_fast_kernel(const __nv_bfloat16* __restrict__ P,
                                                               __nv_bfloat16* __restrict__ dP, int nrows, int T, float scale) {
+  pdl_launch(); pdl_wait();
   const int lane = threadIdx.x & 31;
   const int gr = blockIdx.x * 8 + (threadIdx.x >> 5);
   if (gr >= nrows) return;
@@ -217,17 +221,17 @@ __global__ void __launch_bounds__(256) softmax_bwd_fast_kernel(const __nv_bfloat
 void softmax_causal_fwd(void* s_inout, int nmat, int T, float scale, cudaStream_t s) {
   const int nrows = nmat * T;
   const float sl = scale * 1.4426950408889634f;
-  if (T % 8 == 0 && T <= 1024) softmax_fwd_fast_kernel<4><<<(nrows + 7) / 8, 256, 0, s>>>((__nv_bfloat16*)s_inout, nrows, T, sl);
-  else if (T % 8 == 0 && T <= 2048) softmax_fwd_fast_kernel<8><<<(nrows + 7) / 8, 256, 0, s>>>((__nv_bfloat16*)s_inout, nrows, T, sl);
+  if (T % 8 == 0 && T <= 1024) launch_k(softmax_fwd_fast_kernel<4>, dim3((nrows + 7) / 8), dim3(256), 0, s, (__nv_bfloat16*)s_inout, nrows, T, sl);
+  else if (T % 8 == 0 && T <= 2048) launch_k(softmax_fwd_fast_kernel<8>, dim3((nrows + 7) / 8), dim3(256), 0, s, (__nv_bfloat16*)s_inout, nrows, T, sl);
   else softmax_causal_fwd_generic(s_inout, nmat, T, scale, s);
 }
 
 void softmax_causal_bwd(const void* p, void* dp_inout, int nmat, int T, float scale, cudaStream_t s) {
   const int nrows = nmat * T;
   if (T % 8 == 0 && T <= 1024)
-    softmax_bwd_fast_kernel<4><<<(nrows + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)p, (__nv_bfloat16*)dp_inout, nrows, T, scale);
+    launch_k(softmax_bwd_fast_kernel<4>, dim3((nrows + 7) / 8), dim3(256), 0, s, (const __nv_bfloat16*)p, (__nv_bfloat16*)dp_inout, nrows, T, scale);
   else if (T % 8 == 0 && T <= 2048)
-    softmax_bwd_fast_kernel<8><<<(nrows + 7) / 8, 256, 0, s>>>((const __nv_bfloat16*)p, (__nv_bfloat16*)dp_inout, nrows, T, scale);
+    launch_k(softmax_bwd_fast_kernel<8>, dim3((nrows + 7) / 8), dim3(256), 0, s, (const __nv_bfloat16*)p, (__nv_bfloat16*)dp_inout, nrows, T, scale);
   else softmax_causal_bwd_generic(p, dp_inout, nmat, T, scale, s);
 }
 
@@ -235,6 +239,7 @@ void softmax_causal_bwd(const void* p, void* dp_inout, int nmat, int T, float sc
 // out[i] = sum_s ws[s][i]   (split-K reduction, fp32 slices -> bf16)
 // =====================================================================================================
 __global__ void sum_slices_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ out, int64_t n, int S) {
+  pdl_launch(); pdl_wait();
   const int64_t nvec = n >> 3;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -257,7 +262,7 @@ void sum_slices(const float* ws, void* out, int64_t n, int S, cudaStream_t s) {
   int64_t blocks = (n / 8 + 255) / 256;
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  sum_slices_kernel<<<(int)blocks, 256, 0, s>>>(ws, (__nv_bfloat16*)out, n, S);
+  launch_k(sum_slices_kernel, dim3((int)blocks), dim3(256), 0, s, ws, (__nv_bfloat16*)out, n, S);
 }
 
 }  // namespace tds

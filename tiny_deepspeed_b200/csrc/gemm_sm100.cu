@@ -88,6 +88,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch();   // the next kernel may start its own prologue as soon as every CTA of this grid got here
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
@@ -110,6 +111,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const uint32_t cta_rank = g.cm > 1 ? ptx::cluster_ctarank() : 0u;
   const uint16_t cta_mask = (uint16_t)((1u << g.cm) - 1u);
   if (g.cm > 1) ptx::cluster_sync();   // peers' barriers exist before any multicast / remote commit targets them
+  pdl_wait();     // everything above overlapped the previous kernel's tail; from here on we touch its outputs
 
   const int m_tiles = (g.M + BM - 1) / BM;
   const int n_tiles = (g.N + BN - 1) / BN;
@@ -484,7 +486,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   }
   if (g.cm == 1) {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    gemm_kernel<BN><<<grid, kThreads, Cfg<BN>::kSmem, s>>>(ta, tb, td, tx, g);
+    launch_k(gemm_kernel<BN>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
     return;
   }
   // cluster launch: cm consecutive CTAs = cm consecutive M tiles of one N tile; grid is a whole number of clusters
@@ -496,10 +498,12 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = Cfg<BN>::kSmem;
   cfg.stream = s;
-  cudaLaunchAttribute at[1];
+  cudaLaunchAttribute at[2];
   at[0].id = cudaLaunchAttributeClusterDimension;
   at[0].val.clusterDim.x = g.cm; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-  cfg.attrs = at; cfg.numAttrs = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 2;
   cudaLaunchKernelEx(&cfg, gemm_kernel<BN>, ta, tb, td, tx, g);
 }
 

@@ -9,8 +9,9 @@
 
 namespace tds {
 
-__global__ void step_inc_kernel(int* p) { *p += 1; }
-void step_increment(int* step_ptr, cudaStream_t s) { step_inc_kernel<<<1, 1, 0, s>>>(step_ptr); }
+__global__ void step_inc_kernel(int* p) {
+  pdl_launch(); pdl_wait(); *p += 1; }
+void step_increment(int* step_ptr, cudaStream_t s) { launch_k(step_inc_kernel, dim3(1), dim3(1), 0, s, step_ptr); }
 
 TDS_DEVICE int find_tensor(const int* blk_start, int count, int b) {
   int lo = 0, hi = count - 1;
@@ -58,6 +59,7 @@ TDS_DEVICE void adam_math(float& w, float g, float& m, float& v, float* vmax, co
 template <typename T>
 __global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant__ TensorList tl,
                                                           const __grid_constant__ AdamHyper h) {
+  pdl_launch(); pdl_wait();
   __shared__ float s_bc[2];
   __shared__ int s_t;
   if (threadIdx.x == 0) {
@@ -111,13 +113,14 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant_
 void adamw_multi(const TensorList& tl, const AdamHyper& h, int dtype, cudaStream_t s) {
   const int blocks = tl.blk_start[tl.count];
   if (blocks == 0) return;
-  if (dtype == kBF16) adamw_multi_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(tl, h);
-  else adamw_multi_kernel<float><<<blocks, 256, 0, s>>>(tl, h);
+  if (dtype == kBF16) launch_k(adamw_multi_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, s, tl, h);
+  else launch_k(adamw_multi_kernel<float>, dim3(blocks), dim3(256), 0, s, tl, h);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ TensorList tl,
                                                         const __grid_constant__ SgdHyper h) {
+  pdl_launch(); pdl_wait();
   __shared__ int s_t, s_first;
   if (threadIdx.x == 0) {
     s_t = find_tensor(tl.blk_start, tl.count, blockIdx.x);
@@ -152,8 +155,8 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ 
 void sgd_multi(const TensorList& tl, const SgdHyper& h, int dtype, cudaStream_t s) {
   const int blocks = tl.blk_start[tl.count];
   if (blocks == 0) return;
-  if (dtype == kBF16) sgd_multi_kernel<__nv_bfloat16><<<blocks, 256, 0, s>>>(tl, h);
-  else sgd_multi_kernel<float><<<blocks, 256, 0, s>>>(tl, h);
+  if (dtype == kBF16) launch_k(sgd_multi_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, s, tl, h);
+  else launch_k(sgd_multi_kernel<float>, dim3(blocks), dim3(256), 0, s, tl, h);
 }
 
 }  // namespace tds

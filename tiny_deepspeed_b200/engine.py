@@ -24,7 +24,7 @@ __all__ = ["TrainStep"]
 
 class TrainStep:
     def __init__(self, model, optimizer, *, use_graph: Optional[bool] = None, warmup: int = 3,
-                 grad_sync: bool = True):
+                 grad_sync: bool = True, overlap_step: Optional[bool] = None):
         self.model = model
         self.optimizer = optimizer
         self.grad_sync = grad_sync
@@ -41,6 +41,33 @@ class TrainStep:
         self._seen = 0
         self.steps = 0
         self.launches_per_step = 0
+        if overlap_step is None:
+            import os
+            # measured on B200 (profiles/r1_overlap_pdl.md): 4.87 ms without vs 4.93 ms with -> opt-in
+            overlap_step = os.environ.get("TDS_OVERLAP_STEP", "0") != "0"
+        self.overlap = self._setup_overlap() if (overlap_step and self.device.type == "cuda") else None
+
+    def _setup_overlap(self):
+        """Optimizer-in-backward (optim/overlap.py) where the gradient is final inside backward: single process
+        (no wrapper / world size 1) and native DDP (update chained behind each bucket's NVLS all-reduce)."""
+        from .nn.policy import LocalPolicy
+        from .optim.overlap import StepOverlap
+        from .parallel.wrappers import wrap_layers
+        inner = getattr(self.model, "module", self.model)
+        pol = getattr(self.model, "policy", None)
+        if pol is None:                                    # plain model: give it a private local policy
+            pol = LocalPolicy()
+            wrap_layers(inner, pol)
+            for n, p in inner.named_parameters():
+                p._tds_policy, p._tds_name = pol, n
+        mode, world = getattr(pol, "mode", "ddp"), getattr(pol, "world", 1)
+        native = getattr(pol, "is_native", False)
+        if world > 1 and not (native and mode == "ddp"):
+            return None                                    # ZeRO: the fused reduce->Adam->multicast step handles it
+        ov = StepOverlap(self.optimizer, self.device, stream=pol.comm_stream if native else None)
+        pol.overlap = ov
+        self.optimizer._overlap = ov
+        return ov
 
     # ------------------------------------------------------------------ eager step
     def _eager(self, idx, targets):

@@ -45,12 +45,15 @@ class LocalPolicy(CommPolicy):
     """Single-device behaviour: gradients just accumulate into ``param.grad``."""
 
     name = "local"
+    overlap = None        # optional optim.overlap.StepOverlap (set by engine.TrainStep)
 
     def grad_ready(self, param, grad):
         if param.grad is None:
             param.grad = grad
         elif param.grad.data_ptr() != grad.data_ptr():
             param.grad.add_(grad)
+        if self.overlap is not None and getattr(param, "bwd_sync", True):
+            self.overlap.on_grad(getattr(param, "_tds_name", ""), param)
 
 
 _LOCAL = LocalPolicy()

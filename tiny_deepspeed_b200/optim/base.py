@@ -62,14 +62,26 @@ class Optimizer:
         advancing Adam's bias correction on replay."""
         if getattr(self, "_step_dev", None) is None or self._step_dev.device != device:
             self._step_dev = torch.full((1,), self.step_count - 1, dtype=torch.int32, device=device)
-        from .. import ops
-        ops.ext().step_increment(self._step_dev)
-        ops.count_launch()
+            self._step_dev_for = self.step_count - 1
+        if self._step_dev_for != self.step_count:          # once per step, however many bucket launches follow
+            from .. import ops
+            ops.ext().step_increment(self._step_dev)
+            ops.count_launch()
+            self._step_dev_for = self.step_count
         return self._step_dev
+
+    def _flush_overlap(self):
+        ov = getattr(self, "_overlap", None)
+        if ov is not None:
+            ov.finish()
 
     def step(self):
         self._pending_sync()
-        self.step_count += 1
+        self._flush_overlap()                     # optimizer-in-backward: most tensors were updated during backward
+        if getattr(self, "_overlap_started", False):
+            self._overlap_started = False         # the overlapped launches already opened this step
+        else:
+            self.step_count += 1
         names: List[str] = []
         for name, p in self.parameters.items():
             if not self.owned(name) or p.grad is None:

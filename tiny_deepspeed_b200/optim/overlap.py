@@ -1,0 +1,79 @@
+"""Optimizer-in-backward: hide the (HBM-bound) parameter update under the (latency-bound) backward GEMMs.
+
+The fused Adam kernel moves ~28 bytes per parameter (0.69 ms for GPT-2 small at the HBM roofline) while the backward
+pass at 1x1024 tokens is a chain of short tensor-core kernels that leave most of the memory system idle.  ``StepOverlap``
+updates a bucket of parameters on a side stream as soon as (a) their gradients are final and (b) the backward kernels
+that still READ those parameters (the dX GEMM of the same layer) have been enqueued — which is guaranteed one
+``grad_ready`` later, because every layer issues dW before dX.  ``optimizer.step()`` then only updates whatever is left
+(the embeddings, whose gradients arrive last) and joins the side stream.  Captured into the CUDA graph like everything else.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+
+
+class StepOverlap:
+    def __init__(self, optimizer, device, bucket_bytes: int = 24 << 20, stream: Optional[torch.cuda.Stream] = None):
+        self.opt = optimizer
+        self.device = device
+        self.stream = stream or torch.cuda.Stream(device)
+        self.bucket_bytes = bucket_bytes
+        self.cur: List[str] = []
+        self.cur_bytes = 0
+        self.closed: List[List[str]] = []
+        self.launched_any = False
+        self.stats = {"overlapped_buckets": 0, "overlapped_params": 0}
+
+    # called by the policy right after a parameter's gradient became final (param.grad is set)
+    def on_grad(self, name: str, param) -> None:
+        name = self.opt._canon(name)
+        if name not in self.opt.parameters or not self.opt.owned(name):
+            return
+        # buckets closed before this call are safe now: the dX kernels of their layers are already enqueued
+        while self.closed:
+            self._launch(self.closed.pop(0), overlapped=True)
+        self.cur.append(name)
+        self.cur_bytes += param.grad.numel() * param.grad.element_size() if param.grad is not None else 0
+        if self.cur_bytes >= self.bucket_bytes:
+            self.closed.append(self.cur)
+            self.cur, self.cur_bytes = [], 0
+
+    def _launch(self, names: List[str], overlapped: bool) -> None:
+        opt = self.opt
+        names = [n for n in names if opt.parameters[n].grad is not None]
+        if not names:
+            return
+        if not self.launched_any:
+            opt.step_count += 1                 # this step's counter; optimizer.step() will not bump it again
+            opt._overlap_started = True
+            self.launched_any = True
+        cur = torch.cuda.current_stream(self.device)
+        for n in names:
+            opt._ensure_state(n, opt.parameters[n])
+        if opt.parameters[names[0]].is_cuda:
+            opt._device_step(self.device)       # idempotent per step; on the compute stream, before the fork
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream), torch.no_grad():
+            opt._update(names)
+        for n in names:
+            p = opt.parameters[n]
+            if p.grad is not None and p.grad.is_cuda:
+                p.grad.record_stream(self.stream)
+            p.grad = None
+        if overlapped:
+            self.stats["overlapped_buckets"] += 1
+            self.stats["overlapped_params"] += len(names)
+
+    def finish(self) -> None:
+        """Called from optimizer.step(): flush what is left and make the compute stream wait for all updates."""
+        for b in self.closed:
+            self._launch(b, overlapped=False)
+        self.closed = []
+        if self.cur:
+            self._launch(self.cur, overlapped=False)
+        self.cur, self.cur_bytes = [], 0
+        if self.launched_any:
+            torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        self.launched_any = False

@@ -62,6 +62,8 @@ class DistPolicy(CommPolicy):
             return
         param.bwd_sync = False  # one-shot, re-armed by the wrapper's forward
         if self.world == 1:
+            if getattr(self, "overlap", None) is not None:
+                self.overlap.on_grad(param._tds_name, param)     # gradient is final: update it under backward
             return
         if self.average:
             grad.div_(self.world)

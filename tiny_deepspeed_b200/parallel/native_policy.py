@@ -129,7 +129,10 @@ class NativePolicy(CommPolicy):
         self.stats = {"allreduce_launches": 0, "fused_steps": 0, "bytes": 0}
 
     # ------------------------------------------------------------------------------------------ helpers
+    overlap = None   # optim.overlap.StepOverlap bound to the comm stream (engine.TrainStep sets it for DDP)
+
     def _reset_round(self):
+        self._await_update = []
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._synced_any = False
@@ -162,8 +165,15 @@ class NativePolicy(CommPolicy):
             self._ready[b] += 1
             # the all-reduce only touches the gradient buffer, so a bucket can go the moment its last dW is enqueued;
             # it then runs on the comm stream underneath the remaining dX/dW GEMMs of backward
+            # optimizer-in-backward: buckets whose all-reduce was queued at an EARLIER grad_ready can be updated now
+            # (their layers' dX GEMMs are enqueued); the update runs on the comm stream right behind the all-reduce
+            if self.overlap is not None:
+                for pb in self._await_update:
+                    self.overlap._launch(list(self.buckets[pb]), overlapped=True)
+                self._await_update = []
             if self._ready[b] == len(self.buckets[b]) and not self._launched[b]:
                 self._launch_bucket(b)
+                self._await_update.append(b)
 
     def _launch_complete_buckets(self, flush=False):
         for b, names in enumerate(self.buckets):
