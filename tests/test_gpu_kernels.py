@@ -159,7 +159,7 @@ def test_causal_softmax_and_attention():
     ref.backward(dy.float())
     y, P = ops.causal_attention_forward(qkv, nh)
     _close(y, ref, atol=3e-2)
-    dqkv = ops.causal_attention_backward(dy, qkv, P, nh)
+    dqkv = ops.causal_attention_backward(dy, qkv, P, nh, y=y)
     rel = (dqkv.float() - qf.grad).norm() / qf.grad.norm()
     assert rel < 2e-2, rel
 
@@ -245,3 +245,31 @@ def test_gemm_cluster_multicast(cluster, a_mn, b_mn, cfg):
     got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, config=cfg, cluster=cluster)
     rel = (got.float() - ref).norm() / ref.norm()
     assert rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("B,T,nh", [(1, 128, 2), (2, 384, 3), (1, 1024, 12)])
+def test_flash_attention_kernels(B, T, nh):
+    """Fused tcgen05 flash attention (fwd + bwd) vs fp32 SDPA autograd, and vs our materialised-score path."""
+    C = nh * 64
+    torch.manual_seed(T)
+    qkv = _rand(B, T, 3 * C, scale=0.7)
+    dy = _rand(B, T, C)
+    qf = qkv.float().requires_grad_()
+    q, k, v = (t.view(B, T, nh, 64).transpose(1, 2) for t in qf.split(C, dim=2))
+    ref = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, T, C)
+    ref.backward(dy.float())
+    assert ops.flash_enabled() and ops.ext().flash_supported(T, 64)
+    y, lse = ops.causal_attention_forward(qkv, nh)
+    assert lse.dtype == torch.float32 and lse.shape == (B, nh, T)
+    dqkv = ops.causal_attention_backward(dy, qkv, lse, nh, y=y)
+    assert (y.float() - ref).norm() / ref.norm() < 5e-3
+    assert (dqkv.float() - qf.grad).norm() / qf.grad.norm() < 8e-3
+    ops.set_flash(False)
+    try:
+        y2, P = ops.causal_attention_forward(qkv, nh)
+        d2 = ops.causal_attention_backward(dy, qkv, P, nh, y=y2)
+    finally:
+        ops.set_flash(True)
+    assert P.dtype == torch.bfloat16
+    assert (y.float() - y2.float()).norm() / ref.norm() < 8e-3
+    assert (dqkv.float() - d2.float()).norm() / qf.grad.norm() < 2e-2

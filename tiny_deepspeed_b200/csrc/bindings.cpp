@@ -212,6 +212,37 @@ void colsum_(const Tensor& x, Tensor& out, bool accumulate) {
   check_launch("colsum");
 }
 
+std::vector<Tensor> flash_fwd_(const Tensor& qkv, int64_t n_head) {
+  check_cuda(qkv, "qkv");
+  c10::cuda::CUDAGuard guard(qkv.device());
+  TORCH_CHECK(qkv.dim() == 3 && qkv.is_contiguous() && qkv.scalar_type() == at::kBFloat16);
+  const int B = qkv.size(0), T = qkv.size(1), C = qkv.size(2) / 3, hs = C / (int)n_head;
+  TORCH_CHECK(flash_supported(T, hs), "flash attention needs head size 64 and T % 128 == 0");
+  Tensor y = torch::empty({B, T, C}, qkv.options());
+  Tensor lse = torch::empty({B, n_head, T}, qkv.options().dtype(at::kFloat));
+  flash_fwd(qkv.data_ptr(), y.data_ptr(), lse.data_ptr<float>(), B, T, (int)n_head, 1.0f / sqrtf((float)hs), cur_stream());
+  check_launch("flash_fwd");
+  return {y, lse};
+}
+
+Tensor flash_bwd_(const Tensor& dy, const Tensor& qkv, const Tensor& y, const Tensor& lse, int64_t n_head) {
+  check_cuda(qkv, "qkv");
+  c10::cuda::CUDAGuard guard(qkv.device());
+  TORCH_CHECK(qkv.is_contiguous() && y.is_contiguous() && dy.is_contiguous() && lse.is_contiguous());
+  TORCH_CHECK(qkv.scalar_type() == at::kBFloat16 && y.scalar_type() == at::kBFloat16 && dy.scalar_type() == at::kBFloat16 &&
+              lse.scalar_type() == at::kFloat);
+  const int B = qkv.size(0), T = qkv.size(1), C = qkv.size(2) / 3, hs = C / (int)n_head;
+  TORCH_CHECK(flash_supported(T, hs));
+  Tensor dqkv = torch::empty_like(qkv);
+  auto fopt = qkv.options().dtype(at::kFloat);
+  Tensor dsum = torch::empty({B, n_head, T}, fopt);
+  Tensor dq_ws = torch::empty({B, n_head, T, hs}, fopt);
+  flash_bwd(qkv.data_ptr(), y.data_ptr(), dy.data_ptr(), lse.data_ptr<float>(), dsum.data_ptr<float>(),
+            dq_ws.data_ptr<float>(), dqkv.data_ptr(), B, T, (int)n_head, 1.0f / sqrtf((float)hs), cur_stream());
+  check_launch("flash_bwd");
+  return dqkv;
+}
+
 void sum_slices_(const Tensor& ws, Tensor& out) {
   check_cuda(ws, "ws");
   c10::cuda::CUDAGuard guard(ws.device());
@@ -311,6 +342,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("gelu_bwd", &gelu_bwd_);
   m.def("colsum", &colsum_);
   m.def("sum_slices", &sum_slices_);
+  m.def("flash_fwd", &flash_fwd_);
+  m.def("flash_bwd", &flash_bwd_);
+  m.def("flash_supported", &flash_supported);
   m.def("step_increment", &step_increment_);
   m.def("adamw_multi", &adamw_multi_);
   m.def("sgd_multi", &sgd_multi_);

@@ -1,0 +1,548 @@
+// Fused causal attention for sm_100a (head size 64, T % 128 == 0): tcgen05 + TMEM + TMA, no T x T matrix in HBM.
+//
+// Forward, one CTA per (128-query block, head, batch):
+//   warp 0    TMA producer: Q once, then the K_j / V_j blocks of 128 keys through a 2-stage ring
+//   warp 1    MMA issuer:   S_j = Q K_j^T  (UMMA 128x128x16, 4 k-steps)  -> TMEM S[j&1]
+//                           PV_j = P_j V_j (UMMA 128x64x16, 8 k-steps, V consumed MN-major) -> TMEM PV[j&1]
+//             S_{j+1} is issued before PV_j so the tensor core works underneath the softmax of block j
+//   warps 2-5 softmax / correction / epilogue: thread == query row (tcgen05.ld 32x32b), online softmax in the
+//             log2 domain, P_j written as bf16 into 128B-swizzled smem (the A operand of PV_j), running output
+//             kept in registers (O = O * alpha + PV_j), final O / l through swizzled smem + TMA store, LSE to HBM
+// Only the diagonal block is masked; blocks above the diagonal are never touched.
+//
+// Replaces the reference's standard_attention (example/model.py:29-42: QK^T, mask, softmax, PV as four ATen ops
+// with a materialised [B,nh,T,T] score tensor) and the SDPA fallback.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "common.cuh"
+#include "kernels.h"
+#include "sm100_ptx.cuh"
+#include "tma_util.h"
+
+namespace tds {
+
+namespace {
+
+constexpr int FB = 128;          // query rows per CTA == keys per KV block
+constexpr int HS = 64;           // head size
+constexpr int kFThreads = 192;
+constexpr uint32_t kTileQK = FB * HS * 2;        // 16 KB: one [128 x 64] bf16 tile
+constexpr uint32_t kTileP = FB * FB * 2;         // 32 KB: P as two K-major 64-column slabs
+constexpr uint32_t kFwdSmem = kTileQK * 5 + kTileP * 2 + 1024 + 256;
+
+struct FlashDev {
+  int T, nh;
+  float cs;        // softmax scale * log2(e)
+  float* lse;      // [B, nh, T]  (log2 domain: m * cs + log2(l))
+  uint32_t idesc_s, idesc_pv;
+};
+
+__global__ void __launch_bounds__(kFThreads, 1)
+flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                 const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_o,
+                 const __grid_constant__ FlashDev g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sQ = base;
+  const uint32_t sK = sQ + kTileQK;               // 2 stages
+  const uint32_t sV = sK + 2 * kTileQK;           // 2 stages
+  const uint32_t sP = sV + 2 * kTileQK;           // 2 buffers
+  const uint32_t sBar = sP + 2 * kTileP;
+  enum { Q_FULL = 0, KV_FULL = 1, KV_EMPTY = 3, S_FULL = 5, S_FREE = 7, P_FULL = 9, P_FREE = 11, PV_FULL = 13, PV_FREE = 15, NBAR = 17 };
+  auto bar = [&](int i) { return sBar + 8u * i; };
+  const uint32_t tmem_slot = sBar + 8u * NBAR;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int qb = (int)gridDim.x - 1 - (int)blockIdx.x;    // heaviest (last) query blocks are scheduled first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int n_kv = qb + 1;
+  pdl_launch();
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_q); ptx::prefetch_tmap(&tma_k); ptx::prefetch_tmap(&tma_v); ptx::prefetch_tmap(&tma_o);
+    ptx::mbar_init(bar(Q_FULL), 1);
+    for (int s = 0; s < 2; ++s) {
+      ptx::mbar_init(bar(KV_FULL + s), 1);  ptx::mbar_init(bar(KV_EMPTY + s), 1);
+      ptx::mbar_init(bar(S_FULL + s), 1);   ptx::mbar_init(bar(S_FREE + s), 4);
+      ptx::mbar_init(bar(P_FULL + s), 4);   ptx::mbar_init(bar(P_FREE + s), 1);
+      ptx::mbar_init(bar(PV_FULL + s), 1);  ptx::mbar_init(bar(PV_FREE + s), 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem, tPV = tmem + 256;      // S[2] at columns 0/128, PV[2] at 256/320
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(bar(Q_FULL), kTileQK);
+      ptx::tma_load_4d(sQ, &tma_q, bar(Q_FULL), 0, qb * FB, h, b);
+      for (int j = 0; j < n_kv; ++j) {
+        const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+        ptx::mbar_wait(bar(KV_EMPTY + st), ph ^ 1u);
+        ptx::mbar_expect_tx(bar(KV_FULL + st), 2 * kTileQK);
+        ptx::tma_load_4d(sK + st * kTileQK, &tma_k, bar(KV_FULL + st), 0, j * FB, h, b);
+        ptx::tma_load_4d(sV + st * kTileQK, &tma_v, bar(KV_FULL + st), 0, j * FB, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    auto issue_s = [&](int j) {
+      const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+      ptx::mbar_wait(bar(KV_FULL + st), ph);
+      ptx::mbar_wait(bar(S_FREE + st), ph ^ 1u);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < HS / 16; ++k) {
+          const uint64_t da = ptx::make_smem_desc(sQ + k * 32, 16, 1024);
+          const uint64_t db = ptx::make_smem_desc(sK + st * kTileQK + k * 32, 16, 1024);
+          ptx::mma_f16_ss(tS + st * 128, da, db, g.idesc_s, k > 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(bar(S_FULL + st));
+      }
+      __syncwarp();
+    };
+    ptx::mbar_wait(bar(Q_FULL), 0);
+    issue_s(0);
+    for (int j = 0; j < n_kv; ++j) {
+      if (j + 1 < n_kv) issue_s(j + 1);
+      const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+      ptx::mbar_wait(bar(P_FULL + st), ph);
+      ptx::mbar_wait(bar(PV_FREE + st), ph ^ 1u);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int ks = 0; ks < FB / 16; ++ks) {
+          const uint64_t da = ptx::make_smem_desc(sP + st * kTileP + (ks >> 2) * (FB * 128) + (ks & 3) * 32, 16, 1024);
+          const uint64_t db = ptx::make_smem_desc(sV + st * kTileQK + ks * 2048, FB * 128, 1024);   // MN-major
+          ptx::mma_f16_ss(tPV + st * 64, da, db, g.idesc_pv, ks > 0 ? 1u : 0u);
+        }
+        ptx::mma_commit(bar(PV_FULL + st));
+        ptx::mma_commit(bar(KV_EMPTY + st));
+        ptx::mma_commit(bar(P_FREE + st));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;                 // row inside the 128-query block
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float m = -1e30f, l = 0.f;
+    float o[HS];
+#pragma unroll
+    for (int i = 0; i < HS; ++i) o[i] = 0.f;
+    for (int j = 0; j < n_kv; ++j) {
+      const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
+      const bool diag = (j == qb);
+      ptx::mbar_wait(bar(S_FULL + st), ph);
+      ptx::tc_fence_after();
+      const uint32_t t_s = tS + st * 128 + lane_sel;
+      // pass 1: row maximum (TMEM reads are cheap; two passes keep only 32 values live)
+      float mx = -1e30f;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(t_s + c * 32, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float v = __uint_as_float(raw[i]);
+          if (!diag || c * 32 + i <= row) mx = fmaxf(mx, v);
+        }
+      }
+      const float m_new = fmaxf(m, mx);
+      const float alpha = exp2f((m - m_new) * g.cs);
+      const float mcs = m_new * g.cs;
+      // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
+      ptx::mbar_wait(bar(P_FREE + st), ph ^ 1u);
+      float rs = 0.f;
+      const uint32_t pbuf = sP + st * kTileP;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(t_s + c * 32, raw);
+        ptx::tmem_ld_wait();
+        float p[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float e = exp2f(__uint_as_float(raw[i]) * g.cs - mcs);
+          p[i] = (!diag || c * 32 + i <= row) ? e : 0.f;
+          rs += p[i];
+        }
+        const uint32_t slab = pbuf + (uint32_t)(c >> 1) * (FB * 128) + (uint32_t)row * 128u;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const uint32_t idx = (uint32_t)((c & 1) * 4 + j8);
+          ptx::st_shared_16(slab + ((idx ^ (uint32_t)(row & 7)) << 4), pack8(&p[j8 * 8]));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { ptx::mbar_arrive(bar(S_FREE + st)); ptx::mbar_arrive(bar(P_FULL + st)); }
+      l = l * alpha + rs;
+      m = m_new;
+      // O = O * alpha + P_j V_j
+      ptx::mbar_wait(bar(PV_FULL + st), ph);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tPV + st * 64 + lane_sel + c * 32, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(raw[i]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(PV_FREE + st));
+    }
+    // epilogue: O / l -> bf16 -> swizzled staging (sP[0] is free: every P V has completed) -> TMA store
+    const float inv = 1.f / l;
+    const uint32_t stg = sP + (uint32_t)q * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+    for (int j8 = 0; j8 < 8; ++j8) {
+      float t[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = o[j8 * 8 + i] * inv;
+      ptx::st_shared_16(stg + (((uint32_t)j8 ^ (uint32_t)(lane & 7)) << 4), pack8(t));
+    }
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_4d(&tma_o, sP + (uint32_t)q * 4096u, 0, qb * FB + q * 32, h, b);
+      ptx::bulk_commit();
+    }
+    g.lse[((size_t)b * g.nh + h) * g.T + qb * FB + row] = m * g.cs + log2f(l);
+    if (lane == 0) ptx::bulk_wait_read<0>();
+    __syncwarp();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
+
+// =====================================================================================================
+// Backward.  One CTA per (128-key block j, head, batch) owns dK_j and dV_j (accumulated in TMEM over the query
+// blocks i >= j) and streams Q_i / dO_i through a 2-stage TMA ring.  Per (i, j):
+//     S  = Q_i K_j^T                (UMMA 128x128, K-major / K-major)         -> TMEM
+//     dP = dO_i V_j^T               (UMMA 128x128, K-major / K-major)         -> TMEM
+//     P  = exp2(S*cs - lse_i),  dS = P o (dP - D_i) * scale                   (thread == query row; bf16 -> smem)
+//     dV_j += P^T dO_i,  dK_j += dS^T Q_i   (UMMA 128x64, BOTH operands MN-major: the P/dS/dO/Q tiles as stored)
+//     dQ_i  = dS K_j                (UMMA 128x64, K-major / MN-major) -> fp32 -> TMA reduce-add into the dQ workspace
+// =====================================================================================================
+constexpr uint32_t kBwdSmem = kTileQK * 2 /*K,V*/ + kTileQK * 4 /*Q,dO x2*/ + kTileP * 2 /*P,dS*/ + 32768 /*dQ staging*/ + 1024 + 256;
+
+struct FlashBwdDev {
+  int T, nh;
+  float cs, scale;
+  const float* lse;    // [B, nh, T] log2 domain
+  const float* dsum;   // [B, nh, T]  D = rowsum(dO o O)
+  uint32_t idesc_s, idesc_dkv, idesc_dq;
+};
+
+__global__ void __launch_bounds__(kFThreads, 1)
+flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
+                 const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
+                 const __grid_constant__ CUtensorMap tma_dk, const __grid_constant__ CUtensorMap tma_dv,
+                 const __grid_constant__ CUtensorMap tma_dq, const __grid_constant__ FlashBwdDev g) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t sK = base, sV = sK + kTileQK;
+  const uint32_t sQ = sV + kTileQK;                 // 2 stages
+  const uint32_t sDO = sQ + 2 * kTileQK;            // 2 stages
+  const uint32_t sP = sDO + 2 * kTileQK;
+  const uint32_t sDS = sP + kTileP;
+  const uint32_t sStg = sDS + kTileP;               // 4 warps x 2 x 4 KB (fp32 dQ halves)
+  const uint32_t sBar = sStg + 32768;
+  enum { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, SDP_FULL = 5, SDP_FREE = 6, PDS_FULL = 7, PDS_FREE = 8, DQ_FULL = 9, DQ_FREE = 10, NBAR = 11 };
+  auto bar = [&](int i) { return sBar + 8u * i; };
+  const uint32_t tmem_slot = sBar + 8u * NBAR;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;     // jb = 0 has the most query blocks: scheduled first
+  const int nq = g.T / FB;
+  const int n_it = nq - jb;
+  pdl_launch();
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tma_q); ptx::prefetch_tmap(&tma_k); ptx::prefetch_tmap(&tma_v); ptx::prefetch_tmap(&tma_do);
+    ptx::mbar_init(bar(KV_FULL), 1);
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar(QDO_FULL + s), 1); ptx::mbar_init(bar(QDO_EMPTY + s), 1); }
+    ptx::mbar_init(bar(SDP_FULL), 1); ptx::mbar_init(bar(SDP_FREE), 4);
+    ptx::mbar_init(bar(PDS_FULL), 4); ptx::mbar_init(bar(PDS_FREE), 1);
+    ptx::mbar_init(bar(DQ_FULL), 1);  ptx::mbar_init(bar(DQ_FREE), 4);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tS = tmem, tDP = tmem + 128, tDV = tmem + 256, tDK = tmem + 320, tDQ = tmem + 384;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::mbar_expect_tx(bar(KV_FULL), 2 * kTileQK);
+      ptx::tma_load_4d(sK, &tma_k, bar(KV_FULL), 0, jb * FB, h, b);
+      ptx::tma_load_4d(sV, &tma_v, bar(KV_FULL), 0, jb * FB, h, b);
+      for (int it = 0; it < n_it; ++it) {
+        const int st = it & 1; const uint32_t ph2 = (it >> 1) & 1;
+        ptx::mbar_wait(bar(QDO_EMPTY + st), ph2 ^ 1u);
+        ptx::mbar_expect_tx(bar(QDO_FULL + st), 2 * kTileQK);
+        ptx::tma_load_4d(sQ + st * kTileQK, &tma_q, bar(QDO_FULL + st), 0, (jb + it) * FB, h, b);
+        ptx::tma_load_4d(sDO + st * kTileQK, &tma_do, bar(QDO_FULL + st), 0, (jb + it) * FB, h, b);
+      }
+    }
+  } else if (warp == 1) {
+    ptx::mbar_wait(bar(KV_FULL), 0);
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1; const uint32_t ph2 = (it >> 1) & 1, ph = it & 1;
+      const uint32_t q_s = sQ + st * kTileQK, do_s = sDO + st * kTileQK;
+      ptx::mbar_wait(bar(QDO_FULL + st), ph2);
+      ptx::mbar_wait(bar(SDP_FREE), ph ^ 1u);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < HS / 16; ++k)
+          ptx::mma_f16_ss(tS, ptx::make_smem_desc(q_s + k * 32, 16, 1024), ptx::make_smem_desc(sK + k * 32, 16, 1024),
+                          g.idesc_s, k > 0 ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < HS / 16; ++k)
+          ptx::mma_f16_ss(tDP, ptx::make_smem_desc(do_s + k * 32, 16, 1024), ptx::make_smem_desc(sV + k * 32, 16, 1024),
+                          g.idesc_s, k > 0 ? 1u : 0u);
+        ptx::mma_commit(bar(SDP_FULL));
+      }
+      __syncwarp();
+      ptx::mbar_wait(bar(PDS_FULL), ph);
+      ptx::mbar_wait(bar(DQ_FREE), ph ^ 1u);
+      ptx::tc_fence_after();
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < FB / 16; ++k) {    // reduction over the 128 queries of block i
+          const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
+          ptx::mma_f16_ss(tDV, ptx::make_smem_desc(sP + k * 2048, FB * 128, 1024), ptx::make_smem_desc(do_s + k * 2048, FB * 128, 1024),
+                          g.idesc_dkv, acc);
+          ptx::mma_f16_ss(tDK, ptx::make_smem_desc(sDS + k * 2048, FB * 128, 1024), ptx::make_smem_desc(q_s + k * 2048, FB * 128, 1024),
+                          g.idesc_dkv, acc);
+        }
+#pragma unroll
+        for (int k = 0; k < FB / 16; ++k)      // reduction over the 128 keys of block j
+          ptx::mma_f16_ss(tDQ, ptx::make_smem_desc(sDS + (k >> 2) * (FB * 128) + (k & 3) * 32, 16, 1024),
+                          ptx::make_smem_desc(sK + k * 2048, FB * 128, 1024), g.idesc_dq, k > 0 ? 1u : 0u);
+        ptx::mma_commit(bar(DQ_FULL));
+        ptx::mma_commit(bar(QDO_EMPTY + st));
+        ptx::mma_commit(bar(PDS_FREE));
+      }
+      __syncwarp();
+    }
+  } else {
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t stg = sStg + (uint32_t)q * 8192u;
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = it & 1;
+      const int i = jb + it;
+      const bool diag = (it == 0);
+      const size_t ridx = ((size_t)b * g.nh + h) * g.T + (size_t)i * FB + row;
+      const float lse_r = g.lse[ridx], d_r = g.dsum[ridx];
+      ptx::mbar_wait(bar(SDP_FULL), ph);
+      ptx::tc_fence_after();
+      ptx::mbar_wait(bar(PDS_FREE), ph ^ 1u);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32(tS + lane_sel + c * 32, rs);
+        ptx::tmem_ld_32x32(tDP + lane_sel + c * 32, rp);
+        ptx::tmem_ld_wait();
+        float p[32], ds[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) {
+          const float e = exp2f(__uint_as_float(rs[k]) * g.cs - lse_r);
+          p[k] = (!diag || c * 32 + k <= row) ? e : 0.f;
+          ds[k] = p[k] * (__uint_as_float(rp[k]) - d_r) * g.scale;
+        }
+        const uint32_t off = (uint32_t)(c >> 1) * (FB * 128) + (uint32_t)row * 128u;
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          const uint32_t sw = (((uint32_t)((c & 1) * 4 + j8)) ^ (uint32_t)(row & 7)) << 4;
+          ptx::st_shared_16(sP + off + sw, pack8(&p[j8 * 8]));
+          ptx::st_shared_16(sDS + off + sw, pack8(&ds[j8 * 8]));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) { ptx::mbar_arrive(bar(SDP_FREE)); ptx::mbar_arrive(bar(PDS_FULL)); }
+      // dQ_i contribution of this key block: TMEM -> fp32 staging -> TMA reduce-add
+      ptx::mbar_wait(bar(DQ_FULL), ph);
+      ptx::tc_fence_after();
+      if (lane == 0) ptx::bulk_wait_read<0>();
+      __syncwarp();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tDQ + lane_sel + hf * 32, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          const uint4 v = make_uint4(raw[c16 * 4], raw[c16 * 4 + 1], raw[c16 * 4 + 2], raw[c16 * 4 + 3]);
+          ptx::st_shared_16(stg + hf * 4096u + (uint32_t)lane * 128u + ((((uint32_t)c16) ^ (uint32_t)(lane & 7)) << 4), v);
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        ptx::mbar_arrive(bar(DQ_FREE));
+        const int grow = (int)(((size_t)b * g.nh + h) * g.T) + i * FB + q * 32;
+        ptx::tma_reduce_add_2d(&tma_dq, stg, 0, grow);
+        ptx::tma_reduce_add_2d(&tma_dq, stg + 4096u, 32, grow);
+        ptx::bulk_commit();
+      }
+    }
+    // epilogue: dV_j, dK_j (rows = keys) -> bf16 -> staging -> TMA store into the K / V slices of dqkv
+    if (lane == 0) ptx::bulk_wait_read<0>();
+    __syncwarp();
+#pragma unroll
+    for (int which = 0; which < 2; ++which) {
+      const uint32_t src = which == 0 ? tDV : tDK;
+      const uint32_t dst = stg + (uint32_t)which * 4096u + (uint32_t)lane * 128u;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(src + lane_sel + hf * 32, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) {
+          float t[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) t[k] = __uint_as_float(raw[j8 * 8 + k]);
+          ptx::st_shared_16(dst + ((((uint32_t)(hf * 4 + j8)) ^ (uint32_t)(lane & 7)) << 4), pack8(t));
+        }
+      }
+    }
+    ptx::tc_fence_before();
+    ptx::fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) {
+      ptx::tma_store_4d(&tma_dv, stg, 0, jb * FB + q * 32, h, b);
+      ptx::tma_store_4d(&tma_dk, stg + 4096u, 0, jb * FB + q * 32, h, b);
+      ptx::bulk_commit();
+      ptx::bulk_wait_read<0>();
+    }
+    __syncwarp();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem, 512); }
+}
+
+// D[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one thread per (b,t,h): 8 x 16-byte loads from each tensor)
+__global__ void flash_dsum_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
+                                  float* __restrict__ dsum, int B, int T, int nh) {
+  pdl_launch(); pdl_wait();
+  // 8 lanes per (b,t,h) row: one 16-byte load from each tensor per lane (fully coalesced), 3-step shuffle reduce
+  const int gid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int idx = gid >> 3, v8 = gid & 7;
+  const bool ok = idx < B * T * nh;
+  float acc = 0.f;
+  int hh = 0, t = 0, bb = 0;
+  if (ok) {
+    hh = idx % nh; t = (idx / nh) % T; bb = idx / (nh * T);
+    const size_t off = ((size_t)bb * T + t) * (size_t)(nh * HS) + (size_t)hh * HS + v8 * 8;
+    float a[8], c[8];
+    unpack8(ld8(dout + off), a);
+    unpack8(ld8(out + off), c);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += a[k] * c[k];
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+  acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+  if (ok && v8 == 0) dsum[((size_t)bb * nh + hh) * T + t] = acc;
+}
+
+// dq workspace fp32 [B, nh, T, 64] -> bf16 into dqkv[:, :, h*64 : h*64+64]
+__global__ void flash_dq_convert_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ dqkv, int B, int T, int nh) {
+  pdl_launch(); pdl_wait();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 8 output elements
+  const int per_row = HS / 8;
+  if (idx >= B * nh * T * per_row) return;
+  const int v8 = idx % per_row;
+  const int t = (idx / per_row) % T, hh = (idx / (per_row * T)) % nh, bb = idx / (per_row * T * nh);
+  const float* src = ws + (((size_t)bb * nh + hh) * T + t) * HS + v8 * 8;
+  const float4 a = reinterpret_cast<const float4*>(src)[0], c = reinterpret_cast<const float4*>(src)[1];
+  float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+  st8(dqkv + ((size_t)bb * T + t) * (size_t)(3 * nh * HS) + (size_t)hh * HS + v8 * 8, pack8(f));
+}
+
+}  // namespace
+
+bool flash_supported(int T, int hs) { return hs == HS && T % FB == 0 && T >= FB; }
+
+// dqkv receives dK, dV (TMA stores) and dQ (converted from the fp32 workspace `dq_ws`, which this call zeroes)
+void flash_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, float* dq_ws, void* dqkv,
+               int B, int T, int nh, float scale, cudaStream_t stream) {
+  const int C = nh * HS;
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(dqkv);
+  CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq;
+  auto view = [&](const void* p, int64_t ld, int64_t bs) { return GemmOperand{p, ld, bs, (int64_t)HS, false}; };
+  bool ok = make_map(&tq, view(base, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, FB) &&
+            make_map(&tk, view(base + C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, FB) &&
+            make_map(&tv, view(base + 2 * C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, FB) &&
+            make_map(&tdo, view(dy, C, (int64_t)T * C), T, HS, B, nh, FB) &&
+            make_map(&tdk, view(dbase + C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, 32) &&
+            make_map(&tdv, view(dbase + 2 * C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, 32) &&
+            make_map_f32_2d(&tdq, dq_ws, (int64_t)B * nh * T, HS, HS, 32, 32);
+  if (!ok) { fprintf(stderr, "[tds] flash_bwd: tensor map creation failed\n"); abort(); }
+  cudaMemsetAsync(dq_ws, 0, (size_t)B * nh * T * HS * sizeof(float), stream);
+  const int nthreads = B * T * nh * 8;
+  launch_k(flash_dsum_kernel, dim3((nthreads + 255) / 256), dim3(256), 0, stream, (const __nv_bfloat16*)dy,
+           (const __nv_bfloat16*)y, dsum, B, T, nh);
+  FlashBwdDev g;
+  g.T = T; g.nh = nh; g.cs = scale * 1.4426950408889634f; g.scale = scale; g.lse = lse; g.dsum = dsum;
+  g.idesc_s = make_idesc_bf16(FB, FB, false, false);
+  g.idesc_dkv = make_idesc_bf16(FB, HS, true, true);
+  g.idesc_dq = make_idesc_bf16(FB, HS, false, true);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem); attr = true; }
+  launch_k(flash_bwd_kernel, dim3(T / FB, nh, B), dim3(kFThreads), kBwdSmem, stream, tq, tk, tv, tdo, tdk, tdv, tdq, g);
+  const int nconv = B * nh * T * (HS / 8);
+  launch_k(flash_dq_convert_kernel, dim3((nconv + 255) / 256), dim3(256), 0, stream, (const float*)dq_ws, dbase, B, T, nh);
+}
+
+void flash_fwd(const void* qkv, void* y, float* lse, int B, int T, int nh, float scale, cudaStream_t stream) {
+  const int C = nh * HS;
+  const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv);
+  CUtensorMap tq, tk, tv, to;
+  auto view = [&](const void* p, int64_t ld, int64_t bs) { return GemmOperand{p, ld, bs, (int64_t)HS, false}; };
+  bool ok = make_map(&tq, view(base, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, FB) &&
+            make_map(&tk, view(base + C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, FB) &&
+            make_map(&tv, view(base + 2 * C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, FB) &&
+            make_map(&to, view(y, C, (int64_t)T * C), T, HS, B, nh, 32);
+  if (!ok) { fprintf(stderr, "[tds] flash_fwd: tensor map creation failed\n"); abort(); }
+  FlashDev g;
+  g.T = T; g.nh = nh; g.cs = scale * 1.4426950408889634f; g.lse = lse;
+  g.idesc_s = make_idesc_bf16(FB, FB, false, false);
+  g.idesc_pv = make_idesc_bf16(FB, HS, false, true);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(flash_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFwdSmem); attr = true; }
+  launch_k(flash_fwd_kernel, dim3(T / FB, nh, B), dim3(kFThreads), kFwdSmem, stream, tq, tk, tv, to, g);
+}
+
+}  // namespace tds

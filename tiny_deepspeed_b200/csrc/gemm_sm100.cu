@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "kernels.h"
 #include "sm100_ptx.cuh"
+#include "tma_util.h"
 
 namespace tds {
 
@@ -414,8 +415,8 @@ static EncodeTiledFn get_encode() {
 }
 
 // 4-D map over one bf16 operand: dims (inner, rows, nb2, nb1)
-static bool make_map(CUtensorMap* out, const GemmOperand& op, int rows_mn, int K, int nb1, int nb2, int box_rows_kmajor,
-                     int box_krows_mnmajor = BK) {
+bool make_map(CUtensorMap* out, const GemmOperand& op, int rows_mn, int K, int nb1, int nb2, int box_rows_kmajor,
+              int box_krows_mnmajor) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[4];
@@ -441,6 +442,20 @@ static bool make_map(CUtensorMap* out, const GemmOperand& op, int rows_mn, int K
             (unsigned long long)strides[2], op.ptr);
     return false;
   }
+  return true;
+}
+
+// 2-D fp32 map (cols contiguous), SWIZZLE_128B, box (box_cols <= 32, box_rows): used for TMA reduce-add of fp32 tiles
+bool make_map_f32_2d(CUtensorMap* out, void* ptr, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { fprintf(stderr, "[tds] cuTensorMapEncodeTiled(f32) failed (%d)\n", (int)r); return false; }
   return true;
 }
 

@@ -55,6 +55,12 @@ void gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, cud
 void colsum(const void* x, void* out, bool accumulate, int M, int N, int dtype, cudaStream_t s);
 void sum_slices(const float* ws, void* out_bf16, int64_t n, int S, cudaStream_t s);   // split-K fold (fast_rows.cu)
 
+// ---- fused causal attention (flash_sm100.cu): head size 64, T % 128 == 0 -------------------------------------------
+bool flash_supported(int T, int hs);
+void flash_fwd(const void* qkv, void* y, float* lse_log2, int B, int T, int nh, float scale, cudaStream_t s);
+void flash_bwd(const void* qkv, const void* y, const void* dy, const float* lse_log2, float* dsum_scratch, float* dq_ws,
+               void* dqkv, int B, int T, int nh, float scale, cudaStream_t s);
+
 // ---- optimizers (optim.cu) ---------------------------------------------------------------------------
 constexpr int kMaxTensorsPerLaunch = 320;
 struct TensorList {

@@ -79,6 +79,12 @@ TDS_PTX void tma_store_4d(const CUtensorMap* m, uint32_t src_smem, int c0, int c
                ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
                : "memory");
 }
+// element-wise add of a smem tile into global memory, performed by the TMA/L2 (no register traffic, no atomics in SASS)
+TDS_PTX void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src_smem, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(src_smem), "r"(c0), "r"(c1)
+               : "memory");
+}
 TDS_PTX void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> TDS_PTX void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <typename T16> TDS_PTX void st_shared_16(uint32_t addr, const T16& v) {

@@ -246,15 +246,15 @@ class GELU(tnn.GELU):
 class _AttnFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, qkv, n_head):
-        y, P = ops.causal_attention_forward(qkv, n_head)
+        y, aux = ops.causal_attention_forward(qkv, n_head)      # aux: LSE (flash kernels) or P (materialised path)
         ctx.n_head = n_head
-        ctx.save_for_backward(qkv, P)
+        ctx.save_for_backward(qkv, aux, y)
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        qkv, P = ctx.saved_tensors
-        return ops.causal_attention_backward(dy.contiguous(), qkv, P, ctx.n_head), None
+        qkv, aux, y = ctx.saved_tensors
+        return ops.causal_attention_backward(dy.contiguous(), qkv, aux, ctx.n_head, y=y), None
 
 
 def causal_self_attention(qkv: torch.Tensor, n_head: int) -> torch.Tensor:

@@ -12,6 +12,7 @@ implementations below, which double as the fp32 oracle for the GPU numerics test
 from __future__ import annotations
 
 import math
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -347,6 +348,19 @@ def gelu_backward(grad_output, x):
 # Causal self-attention on a packed qkv buffer
 # --------------------------------------------------------------------------------------
 
+_flash = os.environ.get("TDS_FLASH", "1") != "0"
+
+
+def flash_enabled() -> bool:
+    return _flash
+
+
+def set_flash(flag: bool) -> None:
+    """Switch between the fused flash-attention kernels and the materialised-score GEMM path (both ours)."""
+    global _flash
+    _flash = bool(flag)
+
+
 def _split_heads(qkv, n_head):
     B, T, C3 = qkv.shape
     C = C3 // 3
@@ -365,6 +379,11 @@ def causal_attention_forward(qkv, n_head):
     C = C3 // 3
     hs = C // n_head
     scale = 1.0 / math.sqrt(hs)
+    if on_gpu(qkv) and flash_enabled() and qkv.is_contiguous() and ext().flash_supported(T, hs):
+        # fused tcgen05 flash kernel: no T x T tensor; the second return value is the log2-domain LSE [B,nh,T] (fp32)
+        y, lse = ext().flash_fwd(qkv, n_head)
+        count_launch()
+        return y, lse
     q, k, v = _split_heads(qkv, n_head)
     if on_gpu(qkv):
         S = torch.empty(B, n_head, T, T, device=qkv.device, dtype=qkv.dtype)
@@ -382,9 +401,14 @@ def causal_attention_forward(qkv, n_head):
     return y.to(qkv.dtype), P.to(qkv.dtype)
 
 
-def causal_attention_backward(grad_y, qkv, P, n_head):
-    """Backward of :func:`causal_attention_forward`; returns ``dqkv [B,T,3C]`` written in place by
-    four batched GEMMs (dP, dQ, dK, dV) and one softmax-backward kernel."""
+def causal_attention_backward(grad_y, qkv, P, n_head, y=None):
+    """Backward of :func:`causal_attention_forward`; returns ``dqkv [B,T,3C]``.  ``P`` is whatever forward returned
+    second: the fp32 LSE (flash path: one fused kernel + tiny prep/convert kernels; needs ``y``) or the bf16
+    probabilities (materialised path: four batched GEMMs and one softmax-backward kernel)."""
+    if P.dtype == torch.float32 and P.dim() == 3 and on_gpu(qkv):
+        dqkv = ext().flash_bwd(grad_y.contiguous(), qkv, y, P, n_head)
+        count_launch(3)
+        return dqkv
     B, T, C3 = qkv.shape
     C = C3 // 3
     hs = C // n_head
