@@ -27,7 +27,7 @@ REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="ddp", choices=["ddp", "zero1", "zero2", "zero3", "single"])
@@ -150,7 +150,7 @@ def run_ours(args):
     # ---- kernel/device-timed arm: inputs already resident, K steps between events ---------------------
     barrier_sync(device)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(gpu_index=local) as clk:
+    with ClockSampler(gpu_index=local, period_s=0.05) as clk:
         e0.record()
         for _ in range(args.steps):
             loss = step(x_dev, y_dev)
@@ -176,7 +176,29 @@ def run_ours(args):
     if per_step_launches is None:
         per_step_launches = (ops.launches() - launches_before) // max(2 * args.steps, 1) if args.no_graph else step.launches_per_step
     tokens = B * T * world
-    peak = torch.cuda.max_memory_allocated(device)
+    pol = getattr(model, "policy", None)
+    symm_bytes = pol.symmetric_bytes() if hasattr(pol, "symmetric_bytes") else 0
+    peak = torch.cuda.max_memory_allocated(device) + symm_bytes       # symmetric (VMM) buffers bypass torch's counters
+    peak = max_over_ranks(float(peak), device)
+
+    # ---- exposed (non-overlapped) communication: same step with every collective stubbed out (timing only) --------
+    exposed_ms = None
+    if world > 1 and hasattr(pol, "comm_stub"):
+        pol.comm_stub = True
+        stub = tds.TrainStep(model, opt, use_graph=not args.no_graph, warmup=2)
+        for _ in range(4):
+            stub(x_dev, y_dev)
+        barrier_sync(device)
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(args.steps):
+            stub(x_dev, y_dev)
+        s1.record()
+        torch.cuda.synchronize(device)
+        stub_ms = max_over_ranks(s0.elapsed_time(s1), device) / args.steps
+        exposed_ms = max(0.0, ms_step - stub_ms)
+        pol.comm_stub = False
+        barrier_sync(device)
     if rank == 0:
         out = {
             "metric": "gpt2_train_tokens_per_sec", "value": tokens / (ms_step * 1e-3), "unit": "tokens/s",
@@ -193,7 +215,8 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(x_host.numel() * 8 + y_host.numel() * 8), "d2h_bytes_per_step": 4},
             "gpu_launches": int(per_step_launches) * args.steps,
             "launches_per_step": int(per_step_launches),
-            "final_loss": final_loss, "peak_hbm_bytes": int(peak),
+            "final_loss": final_loss, "peak_hbm_bytes": int(peak), "symmetric_bytes": int(symm_bytes),
+            "exposed_comm_ms_per_step": exposed_ms,
         }
         emit(out)
     import torch.distributed as dist
@@ -260,7 +283,7 @@ def run_reference(args):
         sys.path.insert(0, ROOT)  # only for the clock sampler utility (host-side, not on the measured path)
         from tiny_deepspeed_b200.utils.timing import ClockSampler
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with ClockSampler(gpu_index=local) as clk:
+        with ClockSampler(gpu_index=local, period_s=0.05) as clk:
             e0.record()
             for _ in range(args.steps):
                 loss = one_step(x_dev, y_dev)

@@ -71,3 +71,26 @@ def test_autotuner_keys_per_op():
     calls.clear()
     t.choose_function([slow, fast], torch.zeros(8), key="unseen")
     assert calls == ["slow"]  # finalized: unseen keys run candidate 0 without measuring
+
+
+def test_inventory_parity_helpers():
+    """Small pieces of the reference inventory: dtype table, conv placeholders,
+    get_init_args, free-function collectives (single process: no-ops that keep semantics)."""
+    import pytest
+    import torch.nn as nn
+    from tiny_deepspeed_b200.ops.utils import supported_acc_dtypes, acc_dtype
+    from tiny_deepspeed_b200.nn.conv import Conv2d
+    from tiny_deepspeed_b200.parallel import get_init_args, sync_grad, desync_grad, sync_param, desync_param_data
+    assert supported_acc_dtypes[torch.bfloat16] is torch.float32 and acc_dtype(torch.int8) is torch.int32
+    with pytest.raises(NotImplementedError):
+        Conv2d(1, 1, 1)
+    a = get_init_args(nn.Linear(3, 5, bias=False))
+    assert a["in_features"] == 3 and a["out_features"] == 5 and a["bias"] is False
+    assert get_init_args(nn.Embedding(7, 2))["num_embeddings"] == 7
+    g = torch.ones(4)
+    assert sync_grad(g) is None and desync_grad(g, 0) is g and desync_grad(g, 1) is None
+    p = nn.Parameter(torch.ones(2, 3))
+    full, h = sync_param(p, rank_id=0)
+    assert full is p and h is None
+    desync_param_data(p, rank_id=1)
+    assert p.numel() == 0 and p._tds_shape == (2, 3)

@@ -44,13 +44,13 @@ class _LinearFn(torch.autograd.Function):
         # tiny_deepspeed/core/zero/ddp/module.py:36-66, minus the cuda.synchronize()).
         if weight.requires_grad:
             _grad_of(pol, weight, lambda out, acc: ops.linear_weight_grad(
-                dy, x, weight, out=out, accumulate=acc, out_dtype=weight.dtype))
+                dy, x, weight, getattr(module, "runtime_tuner", None), out=out, accumulate=acc, out_dtype=weight.dtype))
         if bias is not None and bias.requires_grad:
             _grad_of(pol, bias, lambda out, acc: ops.linear_bias_grad(dy, bias, out=out, accumulate=acc))
         dx = None
         if ctx.needs_input_grad[0]:
             w = pol.acquire(weight, backward=True)
-            dx = ops.linear_input_grad(dy, w)
+            dx = ops.linear_input_grad(dy, w, getattr(module, "runtime_tuner", None))
             pol.release(weight, w)
         return dx, None, None, None, (dy if ctx.has_res else None)
 

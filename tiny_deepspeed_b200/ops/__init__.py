@@ -151,6 +151,17 @@ def gemm_splitk(a, b, splits):
     return out
 
 
+def _gemm_tuned(tuner, key, a, b, **kw):
+    """Route a GEMM through the RuntimeAutoTuner: the candidates are the tile configurations of OUR kernel
+    (heuristic, BN = 64 / 128 / 256), timed with CUDA events and cached per (op key, shapes).  Accumulating calls are
+    never measured (re-running them would add the product several times)."""
+    if tuner is None or not getattr(tuner, "enable", False) or not on_gpu(a, b) or kw.get("accumulate"):
+        return gemm(a, b, **kw)
+    import functools
+    cands = [functools.partial(gemm, config=c) for c in (None, 0, 1, 2)]
+    return tuner.choose_function(cands, a, b, key=key, **kw)
+
+
 def linear_forward(input, weight, bias=None, runtime_tuner=None, *, gelu_aux=None, residual=None):
     """``Y = X @ W^T (+ b)`` (reference ops/linear.py:50-54).
 
@@ -160,11 +171,11 @@ def linear_forward(input, weight, bias=None, runtime_tuner=None, *, gelu_aux=Non
     """
     x2 = _flat2d(input)
     if gelu_aux is not None:
-        y = gemm(x2, weight, bias=bias, aux=_flat2d(gelu_aux), epi=EPI_GELU_SAVE)
+        y = _gemm_tuned(runtime_tuner, "linear_fwd_gelu", x2, weight, bias=bias, aux=_flat2d(gelu_aux), epi=EPI_GELU_SAVE)
     elif residual is not None:
-        y = gemm(x2, weight, bias=bias, aux=_flat2d(residual), epi=EPI_RESIDUAL)
+        y = _gemm_tuned(runtime_tuner, "linear_fwd_res", x2, weight, bias=bias, aux=_flat2d(residual), epi=EPI_RESIDUAL)
     else:
-        y = gemm(x2, weight, bias=bias)
+        y = _gemm_tuned(runtime_tuner, "linear_fwd", x2, weight, bias=bias)
     return y.view(*input.shape[:-1], weight.shape[0])
 
 
@@ -179,7 +190,7 @@ def linear_input_grad(grad_output, weight, runtime_tuner=None, *, gelu_aux=None)
     elif on_gpu(dy2) and weight.shape[0] >= 8192 and _splitk_factor(dy2.shape[0], weight.shape[1], weight.shape[0]) > 1:
         dx = gemm_splitk(dy2, weight, _splitk_factor(dy2.shape[0], weight.shape[1], weight.shape[0]))
     else:
-        dx = gemm(dy2, weight, b_mn=True)
+        dx = _gemm_tuned(runtime_tuner, "linear_dx", dy2, weight, b_mn=True)
     return dx.view(*grad_output.shape[:-1], weight.shape[1])
 
 
@@ -191,8 +202,8 @@ def linear_weight_grad(grad_output, input, weight=None, runtime_tuner=None, *, o
     buffer, which is what the comm policies hand in.
     """
     dy2, x2 = _flat2d(grad_output), _flat2d(input)
-    return gemm(dy2, x2, a_mn=True, b_mn=True, out=out, accumulate=accumulate,
-                out_dtype=out_dtype or (weight.dtype if weight is not None else input.dtype))
+    return _gemm_tuned(runtime_tuner, "linear_dw", dy2, x2, a_mn=True, b_mn=True, out=out, accumulate=accumulate,
+                       out_dtype=out_dtype or (weight.dtype if weight is not None else input.dtype))
 
 
 def linear_bias_grad(grad_output, bias=None, runtime_tuner=None, *, out=None, accumulate=False):

@@ -5,6 +5,8 @@ from .optim import (DDPSGD, DDPAdamW, Zero1SGD, Zero1AdamW, Zero2SGD, Zero2AdamW
 from .dist_policy import DistPolicy, shard_parameters_
 from .meta import materialize_, init_tensor_
 from .params import Parameter
+from .wrappers import get_init_args
+from .functional import sync_grad, desync_grad, sync_param, desync_param, desync_param_data
 
 __all__ = ["partition_tensors", "partition_report", "DDP", "Zero1", "Zero2", "Zero3", "wrap_layers",
            "error_handling", "target_modules", "DDPSGD", "DDPAdamW", "Zero1SGD", "Zero1AdamW",

@@ -127,6 +127,21 @@ class NativePolicy(CommPolicy):
         self._accumulated = set()      # names holding un-synced micro-batch gradients
         self._opt_state = None
         self.stats = {"allreduce_launches": 0, "fused_steps": 0, "bytes": 0}
+        # "exposed communication" meter: with the stub on, every collective is skipped / made rank-local,
+        # so (step time) - (stubbed step time) is the communication the overlap did not hide.  Timing only: the
+        # numerics of a stubbed step are meaningless.
+        self.comm_stub = False
+        ext = ops.ext()
+        self._solo_ctx = ext.CommCtx([int(self.comm.flags.peer_ptrs[self.rank])], 0, 1, self.comm.error)
+        self._solo_g = ext.SymmBuf([int(self.G.peer_ptrs[self.rank])], 0)
+        self._solo_p = ext.SymmBuf([int(self.P.peer_ptrs[self.rank])], 0)
+
+    def symmetric_bytes(self) -> int:
+        """HBM held in symmetric allocations (not visible to torch's caching-allocator statistics)."""
+        n = self.G.local.numel() + self.P.local.numel() + self.comm.flags.local.numel()
+        if hasattr(self, "S"):
+            n += self.S.local.numel()
+        return int(n)
 
     # ------------------------------------------------------------------------------------------ helpers
     overlap = None   # optim.overlap.StepOverlap bound to the comm stream (engine.TrainStep sets it for DDP)
@@ -188,8 +203,9 @@ class NativePolicy(CommPolicy):
         hi = max(self.goff[n] + _pad(self.numel[n]) for n in names)
         cur = torch.cuda.current_stream(self.device)
         self.comm_stream.wait_stream(cur)
-        with torch.cuda.stream(self.comm_stream):
-            self.comm.allreduce(self.G, lo, hi - lo, scale=self.scale, blocks=self.comm_blocks, channel=0)
+        if not self.comm_stub:
+            with torch.cuda.stream(self.comm_stream):
+                self.comm.allreduce(self.G, lo, hi - lo, scale=self.scale, blocks=self.comm_blocks, channel=0)
         self._launched[b] = True
         self.stats["allreduce_launches"] += 1
         self.stats["bytes"] += (hi - lo) * 2
@@ -256,9 +272,10 @@ class NativePolicy(CommPolicy):
         # optimizer update of the source tensor are therefore complete when the owner starts writing
         self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.comm_stream):
-            ops.ext().comm_push(self.comm.ctx, int(src), self.S.buf, slot * self.slot_bytes, _pad(self.numel[n]) * 2,
-                                owner, self.comm_blocks, 2)
-            ops.count_launch()
+            if not self.comm_stub:
+                ops.ext().comm_push(self.comm.ctx, int(src), self.S.buf, slot * self.slot_bytes, _pad(self.numel[n]) * 2,
+                                    owner, self.comm_blocks, 2)
+                ops.count_launch()
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
         self._fetched[pos] = ev
@@ -313,8 +330,9 @@ class NativePolicy(CommPolicy):
         st = self._ensure_opt_state(opt)
         opt.step_count += 1
         step_dev = opt._device_step(self.device)
+        ctx, gbuf, pbuf = (self._solo_ctx, self._solo_g, self._solo_p) if self.comm_stub else (self.comm.ctx, self.G.buf, self.P.buf)
         launches = ops.ext().comm_zero_fused_adam(
-            self.comm.ctx, self.G.buf, self.P.buf, st["ranges"], st["master"], st["m"], st["v"],
+            ctx, gbuf, pbuf, st["ranges"], st["master"], st["m"], st["v"],
             float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
             bool(opt.decoupled), bool(opt.maximize), float(opt.grad_scale * self.scale),
             self.mode != "zero3", 1)

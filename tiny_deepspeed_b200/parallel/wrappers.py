@@ -25,7 +25,7 @@ from .. import nn as tds_nn
 from .dist_policy import DistPolicy, shard_parameters_
 from .meta import materialize_
 
-__all__ = ["DDP", "Zero1", "Zero2", "Zero3", "wrap_layers", "error_handling", "target_modules"]
+__all__ = ["DDP", "Zero1", "Zero2", "Zero3", "wrap_layers", "error_handling", "target_modules", "get_init_args"]
 
 
 def target_modules():
@@ -42,6 +42,22 @@ def wrap_layers(model: tnn.Module, policy=None, **_ignored) -> tnn.Module:
         if isinstance(m, ours):
             m.policy = policy
     return model
+
+
+def get_init_args(module: tnn.Module) -> dict:
+    """Constructor arguments that would rebuild ``module`` (reference zero/utils/wrapper.py:46-80).  The engine no
+    longer rebuilds layers (they are adopted in place) but the helper is kept for users of the reference API."""
+    if isinstance(module, tnn.Linear):
+        return dict(in_features=module.in_features, out_features=module.out_features, bias=module.bias is not None,
+                    device=module.weight.device, dtype=module.weight.dtype)
+    if isinstance(module, tnn.LayerNorm):
+        return dict(normalized_shape=module.normalized_shape, eps=module.eps, elementwise_affine=module.elementwise_affine,
+                    bias=module.bias is not None, device=module.weight.device, dtype=module.weight.dtype)
+    if isinstance(module, tnn.Embedding):
+        return dict(num_embeddings=module.num_embeddings, embedding_dim=module.embedding_dim, padding_idx=module.padding_idx,
+                    max_norm=module.max_norm, norm_type=module.norm_type, scale_grad_by_freq=module.scale_grad_by_freq,
+                    sparse=module.sparse, device=module.weight.device, dtype=module.weight.dtype)
+    raise NotImplementedError(f"unsupported layer type {type(module).__name__}")
 
 
 def error_handling(model: tnn.Module) -> None:
