@@ -36,7 +36,8 @@ def parse():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--backend", default="auto", choices=["auto", "native", "dist"])
     ap.add_argument("--no-graph", action="store_true")
-    ap.add_argument("--partition", default="balanced", choices=["greedy", "contiguous", "balanced"])
+    ap.add_argument("--partition", default=None, choices=["greedy", "contiguous", "balanced"],
+                    help="ownership planner (default: balanced for zero1/2, contiguous for zero3 so a layer is one fetch)")
     return ap.parse_args()
 
 
@@ -108,7 +109,8 @@ def build_ours(args, rank, world, device):
     with torch.device("meta"):
         meta = GPT2Model(cfg)
         parts, _ = tds.partition_tensors(OrderedDict(meta.named_parameters()), ranks_map=ranks_map,
-                                         evenness_priority=0, strategy=args.partition)
+                                         evenness_priority=0,
+                                         strategy=args.partition or ("contiguous" if mode == "zero3" else "balanced"))
     W = {"zero1": tds.Zero1, "zero2": tds.Zero2, "zero3": tds.Zero3}[mode]
     O = {"zero1": tds.Zero1AdamW, "zero2": tds.Zero2AdamW, "zero3": tds.Zero3AdamW}[mode]
     if mode == "zero3":

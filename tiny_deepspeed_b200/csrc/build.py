@@ -72,6 +72,23 @@ def build(verbose: bool = False, force: bool = False) -> Path:
     digest = source_hash()
     if not force and SO_PATH.exists() and HASH_PATH.exists() and HASH_PATH.read_text().strip() == digest:
         return SO_PATH
+    # several ranks of one torchrun job may find a stale library at the same time: serialise, then re-check
+    import fcntl
+    OBJ_DIR.mkdir(exist_ok=True)
+    with open(OBJ_DIR / "build.lock", "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and SO_PATH.exists() and HASH_PATH.exists() and HASH_PATH.read_text().strip() == digest:
+                return SO_PATH
+            return _build_locked(digest, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(digest: str, verbose: bool) -> Path:
+    import torch
+    from torch.utils import cpp_extension as ce
+
     nvcc = nvcc_path()
     if nvcc is None:
         raise RuntimeError("nvcc not found: cannot build the sm_100a extension")
@@ -103,7 +120,7 @@ def build(verbose: bool = False, force: bool = False) -> Path:
         objs = [f.result() for f in futs]
 
     torch_lib = str(Path(torch.__file__).parent / "lib")
-    tmp = SO_PATH.with_suffix(".so.tmp")
+    tmp = SO_PATH.with_suffix(f".so.tmp{os.getpid()}")
     _run(["g++", "-shared", "-o", str(tmp), *map(str, objs), f"-L{torch_lib}", f"-Wl,-rpath,{torch_lib}",
           "-lc10", "-ltorch_cpu", "-ltorch", "-ltorch_python", "-lc10_cuda", "-ltorch_cuda",
           f"-L{cuda_home}/lib64", f"-Wl,-rpath,{cuda_home}/lib64", "-lcudart"], log)

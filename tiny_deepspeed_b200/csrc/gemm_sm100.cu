@@ -11,9 +11,13 @@
 //   warp 1      MMA issuer: one lane issues tcgen05.mma (UMMA 128 x BN x 16), tcgen05.commit frees smem
 //               stages and publishes the accumulator; also owns the TMEM allocation (2 x BN columns)
 //   warps 2-5   epilogue: tcgen05.ld 32x32b (thread == accumulator row), fused bias / GELU / GELU' /
-//               residual / accumulate, 16-byte global stores; overlaps the next tile's MMAs through the
-//               double-buffered TMEM accumulator
-// Ragged edges come for free: TMA zero-fills out-of-bounds loads, the epilogue predicates its stores.
+//               residual, bf16 pack -> 128B-swizzled smem slab -> TMA store (coalesced 128-byte rows; the
+//               first version stored 16 B per thread per row and spent half the kernel in partial-sector
+//               writes, profiles/r1_ncu_summary.md); fp32 / accumulating outputs use direct stores.
+//               Overlaps the next tile's MMAs through the double-buffered TMEM accumulator.
+//   optional    thread-block cluster of cm CTAs = cm consecutive M tiles: each loads 1/cm of the B tile and
+//               TMA-multicasts it to all (UTMALDG.MULTICAST), stage release by multicast tcgen05.commit.
+// Ragged edges come for free: TMA zero-fills out-of-bounds loads and clips out-of-bounds stores.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>

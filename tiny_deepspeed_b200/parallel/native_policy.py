@@ -120,6 +120,7 @@ class NativePolicy(CommPolicy):
         self.fetch = os.environ.get("TDS_ZERO3_FETCH", "push")     # "push": owner multicast + prefetch; "peer": GEMM pulls
         self.lookahead, self.nslots = 2, 4
         self._seq, self._seq_frozen, self._pos, self._fetched = [], False, 0, {}
+        self._groups, self._group_of = [], {}
         if mode == "zero3" and self.fetch == "push" and self.world > 1:
             self.slot_bytes = (max(_pad(v) for v in self.numel.values()) * 2 + 4095) // 4096 * 4096
             self.S = symm.alloc(self.nslots * self.slot_bytes, self.device, group)
@@ -240,51 +241,79 @@ class NativePolicy(CommPolicy):
             t = self.P.peer(owner, self.shape[n], self.dtype, self.poff[n] * 2)
             t._tds_remote = True
             return t
-        # ---- owner-push mode: the owner multicasts the tensor into a staging slot of every rank, up to
-        # `lookahead` uses ahead of the consumer, on the communication stream -----------------------------------
+        # ---- owner-push mode: the owner multicasts a GROUP of consecutively used tensors (a contiguous byte range of
+        # its region, typically one transformer layer) into a staging slot of every rank, up to `lookahead` groups
+        # ahead of the consumer, on the communication stream --------------------------------------------------------
         pos = self._pos
         self._pos += 1
         if self._seq_frozen and (pos >= len(self._seq) or self._seq[pos] != n):
             self._seq_frozen, self._seq, pos = False, [], 0       # use order changed: re-record from here
             self._pos = 1
             self._fetched.clear()
+            self._groups, self._group_of = [], {}
         if not self._seq_frozen:
+            # recording step: one group per use (no lookahead yet)
             self._seq.append(n)
-        if pos not in self._fetched:
-            self._launch_fetch(pos)
+            self._groups.append(dict(first=pos, owner=owner, lo=self.poff[n], hi=self.poff[n] + _pad(self.numel[n])))
+            self._group_of[pos] = len(self._groups) - 1
+        g = self._group_of[pos]
+        if g not in self._fetched:
+            self._launch_fetch(g)
         if self._seq_frozen:
             for la in range(1, self.lookahead + 1):
-                if pos + la < len(self._seq) and (pos + la) not in self._fetched:
-                    self._launch_fetch(pos + la)
-        torch.cuda.current_stream(self.device).wait_event(self._fetched[pos])
+                if g + la < len(self._groups) and (g + la) not in self._fetched:
+                    self._launch_fetch(g + la)
+        torch.cuda.current_stream(self.device).wait_event(self._fetched[g])
         if owner == self.rank:
             return param.data
-        slot = pos % self.nslots
-        nbytes = self.numel[n] * 2
-        return self.S.local[slot * self.slot_bytes: slot * self.slot_bytes + nbytes].view(self.dtype).view(self.shape[n])
+        grp = self._groups[g]
+        off = (g % self.nslots) * self.slot_bytes + (self.poff[n] - grp["lo"]) * 2
+        return self.S.local[off: off + self.numel[n] * 2].view(self.dtype).view(self.shape[n])
 
-    def _launch_fetch(self, pos):
-        n = self._seq[pos]
-        owner = self._owner(n)
-        slot = pos % self.nslots
-        src = self.params[n].data_ptr() if owner == self.rank else 0
-        # everything enqueued so far on the compute stream precedes the push: the slot's previous reader and the
-        # optimizer update of the source tensor are therefore complete when the owner starts writing
+    def _launch_fetch(self, g):
+        grp = self._groups[g]
+        owner, slot = grp["owner"], g % self.nslots
+        nbytes = (grp["hi"] - grp["lo"]) * 2
+        src = self.pflat.data_ptr() + grp["lo"] * 2 if owner == self.rank else 0
+        # everything enqueued so far on the compute stream precedes the push: the slot's previous readers and the
+        # optimizer update of the source range are therefore complete when the owner starts writing
         self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.comm_stream):
             if not self.comm_stub:
-                ops.ext().comm_push(self.comm.ctx, int(src), self.S.buf, slot * self.slot_bytes, _pad(self.numel[n]) * 2,
-                                    owner, self.comm_blocks, 2)
+                ops.ext().comm_push(self.comm.ctx, int(src), self.S.buf, slot * self.slot_bytes, nbytes, owner,
+                                    self.comm_blocks, 2)
                 ops.count_launch()
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
-        self._fetched[pos] = ev
-        self.stats["bytes"] += self.numel[n] * 2
+        self._fetched[g] = ev
+        self.stats["bytes"] += nbytes
+
+    def _build_groups(self):
+        """Merge the recorded use sequence into fetch groups: consecutive uses owned by the same rank whose byte ranges
+        (in the owner's region) stay within one staging slot and leave gaps of at most `gap` elements."""
+        gap, cap = 1 << 19, min(self.slot_bytes // 2, 8 << 20)      # elements: <= 16 MB per push keeps the pipeline fine-grained
+        groups, group_of = [], {}
+        for pos, n in enumerate(self._seq):
+            lo, hi, owner = self.poff[n], self.poff[n] + _pad(self.numel[n]), self._owner(n)
+            if groups:
+                cur = groups[-1]
+                nlo, nhi = min(cur["lo"], lo), max(cur["hi"], hi)
+                near = lo <= cur["hi"] + gap and hi + gap >= cur["lo"]
+                # a group may be live while the next `lookahead` groups are being written: keep at most 2 uses of
+                # slack by never letting one group span more than a slot
+                if cur["owner"] == owner and near and nhi - nlo <= cap:
+                    cur["lo"], cur["hi"] = nlo, nhi
+                    group_of[pos] = len(groups) - 1
+                    continue
+            groups.append(dict(first=pos, owner=owner, lo=lo, hi=hi))
+            group_of[pos] = len(groups) - 1
+        self._groups, self._group_of = groups, group_of
 
     def _end_round_zero3(self):
         if self.mode == "zero3" and self.fetch == "push":
             if not self._seq_frozen and self._seq:
                 self._seq_frozen = True
+                self._build_groups()
             self._pos = 0
             self._fetched.clear()
 
