@@ -49,13 +49,19 @@ class Optimizer:
 
     # -- stepping ---------------------------------------------------------------------------
     def _pending_sync(self):
-        """Wait (on stream) for gradient collectives still in flight."""
-        seen = set()
+        """Flush gradient collectives.  Returns ``(late_names, policies_to_join)``: tensors whose reduction is still in
+        flight on a communication stream (updated last, after ``join()``) — everything else can be updated now."""
+        seen, late, joins = set(), set(), []
         for p in self.parameters.values():
             pol = getattr(p, "_tds_policy", None)
             if pol is not None and id(pol) not in seen:
                 seen.add(id(pol))
-                pol.finish()
+                if hasattr(pol, "flush_async"):
+                    late |= {self._canon(n) for n in pol.flush_async()}
+                    joins.append(pol)
+                else:
+                    pol.finish()
+        return late, joins
 
     def _device_step(self, device):
         """Device-resident step counter (int32): bumped by a 1-thread kernel so that a captured CUDA graph keeps
@@ -76,7 +82,7 @@ class Optimizer:
             ov.finish()
 
     def step(self):
-        self._pending_sync()
+        late, joins = self._pending_sync()
         self._flush_overlap()                     # optimizer-in-backward: most tensors were updated during backward
         if getattr(self, "_overlap_started", False):
             self._overlap_started = False         # the overlapped launches already opened this step
@@ -88,9 +94,15 @@ class Optimizer:
                 continue
             self._ensure_state(name, p)
             names.append(name)
-        if names:
-            with torch.no_grad():
-                self._update(names)
+        early = [n for n in names if n not in late]
+        tail = [n for n in names if n in late]
+        with torch.no_grad():
+            if early:
+                self._update(early)              # runs while the last all-reduce is still on the wire
+            for pol in joins:
+                pol.join()
+            if tail:
+                self._update(tail)
         self._post_update()
         for p in self.parameters.values():
             self._zero_grad(p)

@@ -49,6 +49,11 @@ class NativePolicy(CommPolicy):
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.average = average
         self.scale = 1.0 / self.world if average else 1.0
+        import os
+        if os.environ.get("TDS_BUCKET_MB"):
+            bucket_bytes = int(float(os.environ["TDS_BUCKET_MB"]) * (1 << 20))
+        if os.environ.get("TDS_COMM_BLOCKS"):
+            comm_blocks = int(os.environ["TDS_COMM_BLOCKS"])
         self.bucket_bytes = bucket_bytes
         self.comm_blocks = comm_blocks
         named = [(n, p) for n, p in model.named_parameters()]
@@ -149,6 +154,7 @@ class NativePolicy(CommPolicy):
 
     def _reset_round(self):
         self._await_update = []
+        self._bucket_event, self._launch_order = {}, []
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._synced_any = False
@@ -196,26 +202,59 @@ class NativePolicy(CommPolicy):
             if self._launched[b]:
                 continue
             if self._ready[b] == len(names) or (flush and self._ready[b] > 0):
-                self._launch_bucket(b)
+                # the flush at the end of backward has the GPU to itself: use every comm block the flag pad allows
+                self._launch_bucket(b, blocks=ops.ext().COMM_MAX_BLOCKS if flush else None)
 
-    def _launch_bucket(self, b):
+    def _launch_bucket(self, b, blocks=None):
         names = self.buckets[b]
         lo = min(self.goff[n] for n in names)
         hi = max(self.goff[n] + _pad(self.numel[n]) for n in names)
         cur = torch.cuda.current_stream(self.device)
         self.comm_stream.wait_stream(cur)
-        if not self.comm_stub:
-            with torch.cuda.stream(self.comm_stream):
-                self.comm.allreduce(self.G, lo, hi - lo, scale=self.scale, blocks=self.comm_blocks, channel=0)
+        with torch.cuda.stream(self.comm_stream):
+            if not self.comm_stub:
+                self.comm.allreduce(self.G, lo, hi - lo, scale=self.scale, blocks=blocks or self.comm_blocks, channel=0)
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+        self._bucket_event[b] = ev
+        self._launch_order.append(b)
         self._launched[b] = True
         self.stats["allreduce_launches"] += 1
         self.stats["bytes"] += (hi - lo) * 2
+
+    def flush_async(self):
+        """DDP: queue the all-reduce of the last (still open) buckets WITHOUT joining the communication stream and
+        return the names whose gradients are therefore not final yet.  The optimizer updates every other tensor
+        first — ~0.5 ms of HBM-bound Adam that hides the final all-reduce (the embedding gradients are produced by
+        the very last backward kernel, so nothing else can overlap it) — then calls :meth:`join`."""
+        if not (self.mode == "ddp" and self.world > 1 and self._synced_any):
+            self.finish()
+            return set()
+        self._launch_complete_buckets(flush=True)
+        if not self._launch_order:
+            return set()
+        # the most recently queued all-reduce (it carries the embedding gradients, produced by the last backward
+        # kernel) is treated as in flight; everything queued before it is ordered in front of the early update by
+        # waiting on the event recorded behind the previous bucket (comm stream is in-order)
+        late_b = self._launch_order[-1]
+        if len(self._launch_order) > 1:
+            torch.cuda.current_stream(self.device).wait_event(self._bucket_event[self._launch_order[-2]])
+        self._join_pending = True
+        return set(self.buckets[late_b])
+
+    def join(self):
+        if getattr(self, "_join_pending", False):
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+            self._join_pending = False
+            self._accumulated.clear()
+            self._reset_round()
 
     def finish(self):
         """Join the communication stream into the compute stream (no host synchronisation)."""
         if self.mode == "ddp" and self.world > 1 and self._synced_any:
             self._launch_complete_buckets(flush=True)
             torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+            self._join_pending = False
             self._accumulated.clear()
             self._reset_round()
         elif self.mode != "ddp" and self._synced_any and self._opt_state is None:
