@@ -1,6 +1,7 @@
 """Layers with policy-driven backward.  See package docstring."""
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
@@ -15,6 +16,43 @@ def _grad_of(policy, param, compute):
     out, acc = policy.grad_out(param)
     g = compute(out, acc)
     policy.grad_ready(param, g)
+
+
+# dW || dX: the two GEMMs of a Linear's backward are independent and, at 1x1024 tokens, each is a single under-filled
+# wave of latency-bound CTAs — so dW is launched on a side stream while dX runs on the current one (fork/join inside
+# the captured graph).  TDS_DUAL_STREAM=0 restores the serial order.
+_DUAL = os.environ.get("TDS_DUAL_STREAM", "1") != "0"
+_side_streams = {}
+
+
+def _side_stream(t: torch.Tensor):
+    if not _DUAL or not t.is_cuda or ops.is_forced_torch():
+        return None
+    key = t.device.index
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(t.device)
+    return _side_streams[key]
+
+
+def _linear_backward(pol, weight, shape, dy, x, tuner, dx_fn):
+    """``dW`` (into the policy's gradient buffer) and ``dx_fn()`` (the dX GEMM); concurrent when possible."""
+    side = _side_stream(dy) if weight.requires_grad else None
+    if side is None:
+        if weight.requires_grad:
+            _grad_of(pol, weight, lambda out, acc: ops.linear_weight_grad(
+                dy, x, weight, tuner, out=out, accumulate=acc, out_dtype=weight.dtype))
+        return dx_fn()
+    out, acc = pol.grad_out(weight)
+    if out is None:                                   # allocate on the CURRENT stream: the optimizer consumes it there
+        out, acc = torch.empty(shape, dtype=weight.dtype, device=dy.device), False
+    cur = torch.cuda.current_stream(dy.device)
+    side.wait_stream(cur)                             # fork: dy (and x) are ready
+    with torch.cuda.stream(side):
+        g = ops.linear_weight_grad(dy, x, weight, tuner, out=out, accumulate=acc, out_dtype=weight.dtype)
+    dx = dx_fn()
+    cur.wait_stream(side)                             # join before anything downstream (collective, optimizer) touches dW
+    pol.grad_ready(weight, g)
+    return dx
 
 
 # ----------------------------------------------------------------------------------------
@@ -40,18 +78,21 @@ class _LinearFn(torch.autograd.Function):
         pol = policy_of(module)
         weight, bias = module.weight, module.bias
         dy = dy.contiguous()
-        # dW first so its collective overlaps the dX GEMM (same ordering idea as the reference,
-        # tiny_deepspeed/core/zero/ddp/module.py:36-66, minus the cuda.synchronize()).
-        if weight.requires_grad:
-            _grad_of(pol, weight, lambda out, acc: ops.linear_weight_grad(
-                dy, x, weight, getattr(module, "runtime_tuner", None), out=out, accumulate=acc, out_dtype=weight.dtype))
+        tuner = getattr(module, "runtime_tuner", None)
         if bias is not None and bias.requires_grad:
             _grad_of(pol, bias, lambda out, acc: ops.linear_bias_grad(dy, bias, out=out, accumulate=acc))
-        dx = None
-        if ctx.needs_input_grad[0]:
+
+        def dx_fn():
+            if not ctx.needs_input_grad[0]:
+                return None
             w = pol.acquire(weight, backward=True)
-            dx = ops.linear_input_grad(dy, w, getattr(module, "runtime_tuner", None))
+            d = ops.linear_input_grad(dy, w, tuner)
             pol.release(weight, w)
+            return d
+
+        # dW and dX are issued together (dW on a side stream); the gradient's collective starts right after
+        # (reference ordering idea, tiny_deepspeed/core/zero/ddp/module.py:36-66, minus the cuda.synchronize()).
+        dx = _linear_backward(pol, weight, (module.out_features, module.in_features), dy, x, tuner, dx_fn)
         return dx, None, None, None, (dy if ctx.has_res else None)
 
 
@@ -90,22 +131,28 @@ class _MLPFn(torch.autograd.Function):
         fc, proj = ctx.fc, ctx.proj
         pf, pp = policy_of(fc), policy_of(proj)
         dy = dy.contiguous()
-        _grad_of(pp, proj.weight, lambda out, acc: ops.linear_weight_grad(
-            dy, act, proj.weight, out=out, accumulate=acc, out_dtype=proj.weight.dtype))
         if proj.bias is not None:
             _grad_of(pp, proj.bias, lambda out, acc: ops.linear_bias_grad(dy, out=out, accumulate=acc))
-        w = pp.acquire(proj.weight, backward=True)
-        dpre = ops.linear_input_grad(dy, w, gelu_aux=pre)
-        pp.release(proj.weight, w)
-        _grad_of(pf, fc.weight, lambda out, acc: ops.linear_weight_grad(
-            dpre, x, fc.weight, out=out, accumulate=acc, out_dtype=fc.weight.dtype))
+
+        def dpre_fn():
+            w = pp.acquire(proj.weight, backward=True)
+            d = ops.linear_input_grad(dy, w, gelu_aux=pre)       # GELU' folded into the dX epilogue
+            pp.release(proj.weight, w)
+            return d
+
+        dpre = _linear_backward(pp, proj.weight, (proj.out_features, proj.in_features), dy, act, None, dpre_fn)
         if fc.bias is not None:
             _grad_of(pf, fc.bias, lambda out, acc: ops.linear_bias_grad(dpre, out=out, accumulate=acc))
-        dx = None
-        if ctx.needs_input_grad[0]:
+
+        def dx_fn():
+            if not ctx.needs_input_grad[0]:
+                return None
             w = pf.acquire(fc.weight, backward=True)
-            dx = ops.linear_input_grad(dpre, w)
+            d = ops.linear_input_grad(dpre, w)
             pf.release(fc.weight, w)
+            return d
+
+        dx = _linear_backward(pf, fc.weight, (fc.out_features, fc.in_features), dpre, x, None, dx_fn)
         return dx, None, None, (dy if ctx.has_res else None)
 
 
