@@ -6,15 +6,20 @@ views over those buffers.
 
 * **DDP** — backward GEMMs write dW straight into the symmetric gradient buffer; as soon as a bucket of
   consecutive tensors is complete a two-shot NVLS all-reduce kernel (``multimem.ld_reduce`` +
-  ``multimem.st``) runs on the communication stream while backward continues.
+  ``multimem.st``) runs on the communication stream while backward continues.  The last bucket (the
+  embedding gradients, produced by the final backward kernel) is hidden under the Adam update of everything
+  that was reduced earlier (``flush_async`` / ``join``).
 * **ZeRO-1/2** — one fused kernel per step on the owner: switch-reduced gradient → scale → Adam on
   the local fp32 master/moments → bf16 parameter multicast to all ranks
   (``csrc/comm_sm100.cu: zero_fused_adam_kernel``).  Non-owners never materialise ``param.grad``.
 * **ZeRO-3** — a tensor is resident on its owner only (the symmetric parameter buffer is sized for the
-  largest owner share, not for the model).  Consumers do not gather it: ``acquire`` hands the layer a
-  tensor that *aliases the owner's memory over NVLink*, and the tcgen05 GEMM's TMA producer streams the
-  weight tiles peer-to-peer straight into shared memory (all-gather fused into the GEMM, nothing staged
-  in local HBM).  Gradients are reduced to the owner by the same fused Adam kernel (no broadcast).
+  largest owner share, not for the model).  ``fetch="push"`` (default): the owner ``multimem.st``-pushes a
+  group of consecutively used tensors (≈ one layer, ≤ 16 MB) into a 4-slot symmetric staging ring on every
+  rank, two groups ahead of the consumer, on the communication stream: each weight crosses NVLink once per
+  pass.  ``fetch="peer"``: ``acquire`` hands the layer a tensor that *aliases the owner's memory over
+  NVLink* and the tcgen05 GEMM's TMA producer streams the weight tiles peer-to-peer straight into shared
+  memory (all-gather fused into the GEMM, nothing staged in HBM; M/128 re-reads of each tile).  Gradients
+  are reduced to the owner by the same fused Adam kernel (no broadcast afterwards).
 
 Synchronisation is device-side (flag pads), the whole step is CUDA-graph capturable, and nothing here
 calls NCCL after construction.
