@@ -171,3 +171,63 @@ def test_ddp_native_under_cuda_graph():
     losses, captured, stats = res[0]
     assert captured and losses[-1] < losses[0]
     assert stats["allreduce_launches"] > 0
+
+
+def _accum_native(rank, world, backend):
+    """Two micro-batches, sync only on the second: the reduced gradient must be the accumulated sum."""
+    import torch.distributed as dist
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    dev = torch.device("cuda", rank)
+    torch.manual_seed(0)
+    cfg = gpt2_config("tiny", n_layer=1, n_embd=128, n_head=2, vocab_size=512, block_size=128)
+    model = tds.DDP(GPT2Model(cfg).to(device=dev, dtype=torch.bfloat16), backend=backend)
+    g = torch.Generator().manual_seed(7 + rank)
+    xs = [torch.randint(0, cfg.vocab_size, (1, 128), generator=g).to(dev) for _ in range(4)]
+    model.require_backward_grad_sync = False
+    _, l = model(xs[0], xs[1]); l.backward()
+    model.require_backward_grad_sync = True
+    _, l = model(xs[2], xs[3]); l.backward()
+    model.finish_grad_sync()
+    torch.cuda.synchronize()
+    p = dict(model.module.named_parameters())["transformer.h.0.attn.c_attn.weight"]
+    return p.grad.float().cpu()
+
+
+def test_native_grad_accumulation_matches_dist():
+    a = run_gpu_distributed(_accum_native, world=2, args=("native",))
+    b = run_gpu_distributed(_accum_native, world=2, args=("dist",))
+    assert torch.equal(a[0], a[1])                           # replicas hold the same reduced gradient
+    rel = (a[0] - b[0]).norm() / b[0].norm()
+    assert rel < 2e-2, float(rel)
+
+
+def _graph_zero(rank, world, mode):
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    dev = torch.device("cuda", rank)
+    cfg = gpt2_config("tiny", n_layer=2, n_embd=256, n_head=4, vocab_size=2048, block_size=128)
+    with torch.device("meta"):
+        parts, _ = tds.partition_tensors(OrderedDict(GPT2Model(cfg).named_parameters()), num_parts=world, strategy="contiguous")
+        model = GPT2Model(cfg).to(torch.bfloat16)
+    W = {"zero1": tds.Zero1, "zero3": tds.Zero3}[mode]
+    O = {"zero1": tds.Zero1AdamW, "zero3": tds.Zero3AdamW}[mode]
+    if mode == "zero3":
+        model = W(model, parts, device=dev, init_seed=1, backend="native")
+    else:
+        from tiny_deepspeed_b200.parallel import materialize_
+        materialize_(model, device=dev, seed=1)
+        model = W(model, parts, backend="native")
+    opt = O(model.module.named_parameters(), lr=1e-3, weight_decay=0.1, param_part_table=parts, ranks_map=[f"cuda:{i}" for i in range(world)])
+    step = tds.TrainStep(model, opt, use_graph=True, warmup=2)
+    x = torch.randint(0, cfg.vocab_size, (2, 128), device=dev)
+    y = torch.randint(0, cfg.vocab_size, (2, 128), device=dev)
+    losses = [float(step(x, y)) for _ in range(8)]
+    return losses, step.graph is not None
+
+
+@pytest.mark.parametrize("mode", ["zero1", "zero3"])
+def test_zero_native_under_cuda_graph(mode):
+    res = run_gpu_distributed(_graph_zero, world=2, args=(mode,))
+    losses, captured = res[0]
+    assert captured and losses[-1] < losses[0] - 0.05, losses

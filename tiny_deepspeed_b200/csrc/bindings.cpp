@@ -118,9 +118,16 @@ Tensor layernorm_bwd_(const Tensor& dy, const Tensor& x, const Tensor& w, const 
   Tensor scratch = torch::empty({layernorm_bwd_scratch_rows(), 2 * N}, x.options().dtype(at::kFloat));
   const void* addp = nullptr;
   if (add.has_value() && add->defined()) { TORCH_CHECK(add->is_contiguous() && add->scalar_type() == x.scalar_type()); addp = add->data_ptr(); }
+  // arrival counter of the single-launch fold (the last CTA resets it to zero): one persistent int per device
+  static std::vector<Tensor> counters(64);
+  const int dev = x.get_device();
+  if (!counters[dev].defined()) counters[dev] = torch::zeros({1}, x.options().dtype(at::kInt));
+  // measured (B200, GPT-2 small step): the single-launch variant costs +0.36 ms/step (one CTA folding 128 x 2N partials is
+  // slower than a second, parallel launch), so the two-kernel form is the default; TDS_LN_SINGLE=1 selects the other.
+  static const bool two_kernels = !(getenv("TDS_LN_SINGLE") && atoi(getenv("TDS_LN_SINGLE")) != 0);
   layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), addp,
                 dx.data_ptr(), scratch.data_ptr<float>(), dw.data_ptr(), db.data_ptr(), accumulate, M, N, dtype_of(x),
-                cur_stream());
+                cur_stream(), two_kernels ? nullptr : counters[dev].data_ptr<int>());
   check_launch("layernorm_bwd");
   return dx;
 }

@@ -23,7 +23,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_fast_kernel(
     const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ w,
     const float* __restrict__ mean, const float* __restrict__ rstd, const __nv_bfloat16* __restrict__ add,
-    __nv_bfloat16* __restrict__ dx, float* __restrict__ scratch, int M, int N) {
+    __nv_bfloat16* __restrict__ dx, float* __restrict__ scratch, int M, int N, int* __restrict__ counter,
+    __nv_bfloat16* __restrict__ dw, __nv_bfloat16* __restrict__ db, int accumulate) {
   pdl_launch(); pdl_wait();
   extern __shared__ float sm[];   // [kRowWarps][2N]
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -88,6 +89,32 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_fast_kernel(
     for (int k = 0; k < kRowWarps; ++k) a += sm[(size_t)k * 2 * N + i];
     out[i] = a;
   }
+  if (counter == nullptr) return;            // two-kernel variant: ln_fold_kernel finishes the job
+  // single-launch variant: the last CTA to arrive folds all per-CTA partials (they are L2-resident: gridDim.x x 2N floats)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1) == (int)gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int P = gridDim.x;
+  for (int col = threadIdx.x; col < 2 * N; col += blockDim.x) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int r = 0;
+    for (; r + 3 < P; r += 4) {
+      a0 += __ldcg(scratch + (size_t)r * 2 * N + col);
+      a1 += __ldcg(scratch + (size_t)(r + 1) * 2 * N + col);
+      a2 += __ldcg(scratch + (size_t)(r + 2) * 2 * N + col);
+      a3 += __ldcg(scratch + (size_t)(r + 3) * 2 * N + col);
+    }
+    for (; r < P; ++r) a0 += __ldcg(scratch + (size_t)r * 2 * N + col);
+    float t = (a0 + a1) + (a2 + a3);
+    __nv_bfloat16* dst = col < N ? dw + col : db + (col - N);
+    if (accumulate) t += __bfloat162float(*dst);
+    *dst = __float2bfloat16_rn(t);
+  }
+  if (threadIdx.x == 0) *counter = 0;        // ready for the next launch
 }
 
 __global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ scratch, __nv_bfloat16* __restrict__ dw,
@@ -114,7 +141,7 @@ __global__ void __launch_bounds__(256) ln_fold_kernel(const float* __restrict__ 
 template <int MAXV>
 static void launch_ln_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                           const void* add, void* dx, float* scratch, void* dw, void* db, bool accumulate, int M, int N,
-                          cudaStream_t s) {
+                          int* counter, cudaStream_t s) {
   int ctas = (M + kRowWarps - 1) / kRowWarps;
   const int cap = layernorm_bwd_scratch_rows();
   if (ctas > cap) ctas = cap;
@@ -123,16 +150,17 @@ static void launch_ln_bwd(const void* dy, const void* x, const void* w, const fl
   if (!attr) { cudaFuncSetAttribute(ln_bwd_fast_kernel<MAXV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr = true; }
   launch_k(ln_bwd_fast_kernel<MAXV>, dim3(ctas), dim3(kRowWarps * 32), smem, s, 
       (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)w, mean, rstd, (const __nv_bfloat16*)add,
-      (__nv_bfloat16*)dx, scratch, M, N);
-  launch_k(ln_fold_kernel, dim3((2 * N + 31) / 32), dim3(256), 0, s, scratch, (__nv_bfloat16*)dw, (__nv_bfloat16*)db, ctas, N, accumulate ? 1 : 0);
+      (__nv_bfloat16*)dx, scratch, M, N, counter, (__nv_bfloat16*)dw, (__nv_bfloat16*)db, accumulate ? 1 : 0);
+  if (counter == nullptr)
+    launch_k(ln_fold_kernel, dim3((2 * N + 31) / 32), dim3(256), 0, s, scratch, (__nv_bfloat16*)dw, (__nv_bfloat16*)db, ctas, N, accumulate ? 1 : 0);
 }
 
 void layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd, const void* add,
                    void* dx, float* scratch, void* dw, void* db, bool accumulate, int M, int N, int dtype,
-                   cudaStream_t s) {
+                   cudaStream_t s, int* counter) {
   if (dtype == kBF16 && N % 8 == 0 && N <= 2048) {
-    if (N <= 1024) launch_ln_bwd<4>(dy, x, w, mean, rstd, add, dx, scratch, dw, db, accumulate, M, N, s);
-    else launch_ln_bwd<8>(dy, x, w, mean, rstd, add, dx, scratch, dw, db, accumulate, M, N, s);
+    if (N <= 1024) launch_ln_bwd<4>(dy, x, w, mean, rstd, add, dx, scratch, dw, db, accumulate, M, N, counter, s);
+    else launch_ln_bwd<8>(dy, x, w, mean, rstd, add, dx, scratch, dw, db, accumulate, M, N, counter, s);
     return;
   }
   layernorm_bwd_generic(dy, x, w, mean, rstd, add, dx, scratch, dw, db, accumulate, M, N, dtype, s);

@@ -139,6 +139,24 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     float o[HS];
 #pragma unroll
     for (int i = 0; i < HS; ++i) o[i] = 0.f;
+    float alpha_prev = 1.f;
+    // O = O * alpha_j + P_j V_j   (alpha_j rescales everything accumulated BEFORE block j)
+    auto o_update = [&](int jj, float a) {
+      const int st2 = jj & 1; const uint32_t ph2 = (jj >> 1) & 1;
+      ptx::mbar_wait(bar(PV_FULL + st2), ph2);
+      ptx::tc_fence_after();
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(tPV + st2 * 64 + lane_sel + c * 32, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * a + __uint_as_float(raw[i]);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(PV_FREE + st2));
+    };
     for (int j = 0; j < n_kv; ++j) {
       const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
       const bool diag = (j == qb);
@@ -190,21 +208,12 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       if (lane == 0) { ptx::mbar_arrive(bar(S_FREE + st)); ptx::mbar_arrive(bar(P_FULL + st)); }
       l = l * alpha + rs;
       m = m_new;
-      // O = O * alpha + P_j V_j
-      ptx::mbar_wait(bar(PV_FULL + st), ph);
-      ptx::tc_fence_after();
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(tPV + st * 64 + lane_sel + c * 32, raw);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * alpha + __uint_as_float(raw[i]);
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(bar(PV_FREE + st));
+      // O update of the PREVIOUS block (software pipelining: P_{j-1} V_{j-1} ran on the tensor core while this
+      // thread was busy with the softmax of block j), then remember this block's rescale factor
+      if (j > 0) o_update(j - 1, alpha_prev);
+      alpha_prev = alpha;
     }
+    o_update(n_kv - 1, alpha_prev);
     // epilogue: O / l -> bf16 -> swizzled staging (sP[0] is free: every P V has completed) -> TMA store
     const float inv = 1.f / l;
     const uint32_t stg = sP + (uint32_t)q * 4096u + (uint32_t)lane * 128u;

@@ -51,6 +51,7 @@ struct GemmDev {
   int a_mn, b_mn;
   int tri;
   int cm;         // cluster size along M (1, 2, 4, 8): B tile fetched once per cluster and multicast
+  int aux_tma;    // aux operand (residual / GELU pre-activation) is read through a tensor map
   int tma_store;  // epilogue goes registers -> swizzled smem -> TMA store (bf16 out, no accumulate, aligned)
   int dbg;      // TDS_GEMM_DBG bits (profiling only): 1 = no global stores, 2 = no MMA issue, 4 = no epilogue body
   uint32_t idesc;
@@ -88,6 +89,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   auto tfull_bar = [&](int s) { return sBar + 8u * (2 * C::kStages + s); };
   auto tempty_bar = [&](int s) { return sBar + 8u * (2 * C::kStages + 2 + s); };
   const uint32_t tmem_slot = sBar + 8u * (2 * C::kStages + 4);
+  auto aux_bar = [&](int w) { return sBar + 8u * (2 * C::kStages + 6 + w); };   // per epilogue warp: aux tile landed
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -103,6 +105,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // cm MMA issuers have released it
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (uint32_t)g.cm); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    for (int w = 0; w < 4; ++w) ptx::mbar_init(aux_bar(w), 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -219,6 +222,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     uint32_t sbuf_toggle = 0;
     const uint32_t my_stage0 = sStage + (uint32_t)q * 2u * kStageBufBytes;   // two 4 KB staging buffers per warp
     const bool gelu_save = g.epi == EPI_GELU_SAVE;
+    const bool aux_in = g.aux_tma && (g.epi == EPI_GELU_BWD || g.epi == EPI_RESIDUAL);   // aux tile arrives by TMA
+    uint32_t aux_phase = 0;
     const bool vec_ok = (g.N % 8 == 0) && (g.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(g.d) & 15) == 0) &&
                         (g.aux == nullptr || (g.ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0));
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -242,9 +247,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const int ns = n0 + slab * 64;
           if (ns >= g.N) break;
           uint32_t dbuf, abuf = 0;
-          if (gelu_save) { dbuf = my_stage0; abuf = my_stage0 + kStageBufBytes; if (lane == 0) ptx::bulk_wait_read<0>(); }
+          if (gelu_save || aux_in) { dbuf = my_stage0; abuf = my_stage0 + kStageBufBytes; if (lane == 0) ptx::bulk_wait_read<0>(); }
           else { dbuf = my_stage0 + sbuf_toggle * kStageBufBytes; sbuf_toggle ^= 1u; if (lane == 0) ptx::bulk_wait_read<1>(); }
           __syncwarp();
+          if (aux_in) {
+            // residual / pre-activation tile (32 rows x 64 cols) by TMA into the second staging buffer: coalesced 128-byte
+            // rows instead of one 16-byte global load per thread per row
+            if (lane == 0) {
+              ptx::mbar_expect_tx(aux_bar(q), kStageBufBytes);
+              ptx::tma_load_4d(abuf, &tma_aux, aux_bar(q), ns, m0 + q * 32, 0, 0);
+            }
+            ptx::mbar_wait(aux_bar(q), aux_phase);
+            aux_phase ^= 1u;
+          }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t raw[32];
@@ -274,7 +289,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 float af[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) af[j] = 0.f;
-                if (row_ok && col_ok) unpack8(ld8(g.aux + (long long)m * g.ld_aux + nc), af);
+                if (aux_in) unpack8(ptx::ld_shared_16<bf16x8>(abuf + chunk), af);     // OOB rows/cols were zero-filled
+                else if (row_ok && col_ok) unpack8(ld8(g.aux + (long long)m * g.ld_aux + nc), af);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                   v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
@@ -570,19 +586,19 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.batch;
   // output through TMA (coalesced 128-byte rows) whenever the layout allows it
   CUtensorMap td = ta, tx = ta;
-  g.tma_store = 0;
+  g.tma_store = 0; g.aux_tma = 0;
   static const int no_tma_store = getenv("TDS_GEMM_DIRECT_STORE") ? atoi(getenv("TDS_GEMM_DIRECT_STORE")) : 0;
   const bool aligned = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) && (p.N % 8 == 0) &&
                        (p.d_batch_stride % 8 == 0) && (p.d_batch_stride2 % 8 == 0);
   if (!no_tma_store && p.d_dtype == kBF16 && !p.accumulate && aligned) {
     GemmOperand od{p.d, p.ldd, p.d_batch_stride, p.d_batch_stride2, false};
     bool ok = make_map(&td, od, p.M, p.N, nb1, nb2, 32);
-    if (ok && g.epi == EPI_GELU_SAVE) {
+    if (ok && g.epi != EPI_NONE) {
       GemmOperand oa{p.aux, p.ld_aux, 0, 0, false};
       ok = (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0) && make_map(&tx, oa, p.M, p.N, 1, 1, 32);
+      static const int no_aux_tma = getenv("TDS_GEMM_AUX_DIRECT") ? atoi(getenv("TDS_GEMM_AUX_DIRECT")) : 0;
+      g.aux_tma = (ok && !no_aux_tma) ? 1 : 0;
     }
-    if (ok && g.epi != EPI_NONE && g.epi != EPI_GELU_SAVE)
-      ok = (p.ld_aux % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 15) == 0);
     g.tma_store = ok ? 1 : 0;
   }
   if (cfg == 0) launch<64>(ta, tb, td, tx, g, (int)tiles, stream);

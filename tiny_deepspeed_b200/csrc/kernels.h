@@ -39,7 +39,7 @@ void layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* 
 int layernorm_bwd_scratch_rows();
 void layernorm_bwd(const void* dy, const void* x, const void* w, const float* mean, const float* rstd,
                    const void* add, void* dx, float* scratch, void* dw, void* db, bool accumulate,
-                   int M, int N, int dtype, cudaStream_t s);
+                   int M, int N, int dtype, cudaStream_t s, int* counter = nullptr);   // counter: zeroed int -> single launch
 void embedding_fwd(const int64_t* idx, const void* weight, const void* add, int add_rows, void* out,
                    int ntok, int dim, int64_t vocab, int dtype, cudaStream_t s);
 void embedding_bwd(const int64_t* idx, const void* dy, void* dw, bool accumulate, int64_t padding_idx,

@@ -93,6 +93,15 @@ template <typename T16> TDS_PTX void st_shared_16(uint32_t addr, const T16& v) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(u.x), "r"(u.y), "r"(u.z), "r"(u.w) : "memory");
 }
 
+template <typename T16> TDS_PTX T16 ld_shared_16(uint32_t addr) {
+  static_assert(sizeof(T16) == 16, "16-byte payload");
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w) : "r"(addr) : "memory");
+  T16 v;
+  *reinterpret_cast<uint4*>(&v) = u;
+  return v;
+}
+
 // ---- tcgen05 ------------------------------------------------------------------------------------------
 TDS_PTX void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");

@@ -256,7 +256,7 @@ def layernorm_bwd(grad_output, input, weight, mean, rstd, *, dw_out=None, db_out
             accumulate = False
         dx = ext().layernorm_bwd(dy2, x2, weight, mean, rstd, dw_out, db_out, bool(accumulate),
                                  None if add_to_dx is None else _flat2d(add_to_dx))
-        count_launch(2)
+        count_launch(1 if os.environ.get("TDS_LN_SINGLE", "0") != "0" else 2)   # row pass + partial fold
         return dx.view_as(input), dw_out, db_out
     dyf, xf = dy2.float(), x2.float()
     xhat = (xf - mean[:, None]) * rstd[:, None]
