@@ -52,7 +52,7 @@ def test_gemm_layouts(M, N, K, a_mn, b_mn):
     assert rel < 5e-3, rel
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 def test_gemm_tile_configs_and_fp32_out(cfg):
     a, b = _rand(384, 512), _rand(640, 512)
     ref = a.float() @ b.float().t()
@@ -234,7 +234,7 @@ def test_splitk_lm_head_input_grad():
 
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True)])
-@pytest.mark.parametrize("cfg", [0, 1, 2])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
 def test_gemm_cluster_multicast(cluster, a_mn, b_mn, cfg):
     """B tile fetched once per cluster of M-tiles and TMA-multicast into all of them."""
     M, N, K = 1024, 1536, 832

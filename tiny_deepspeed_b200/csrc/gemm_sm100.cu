@@ -58,11 +58,11 @@ struct GemmDev {
 };
 
 template <int BN> struct Cfg {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kABytes = BM * BK * 2;   // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kSmem = kStages * (kABytes + kBBytes) + 4 * 2 * 4096 /*epilogue staging*/ + 1024 /*align*/ + 256 /*barriers*/;
-  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN;   // 128 / 256 / 512 : powers of two
+  static constexpr int kTmemCols = BN == 64 ? 128 : (BN == 128 ? 256 : 512);   // power of two >= 2 * BN
 };
 
 __device__ __forceinline__ void tile_k_range(const GemmDev& g, int m0, int nkb, int& kb0, int& kb1) {
@@ -481,14 +481,16 @@ bool make_map_f32_2d(CUtensorMap* out, void* ptr, int64_t rows, int64_t cols, in
 
 static int g_num_sms = 0;
 
-int gemm_num_configs() { return 3; }   // BN = 64, 128, 256
+int gemm_num_configs() { return 4; }   // BN = 64, 128, 256, 192
 
 static int pick_config(const GemmParams& p) {
-  if (p.config >= 0 && p.config < 3) return p.config;
+  if (p.config >= 0 && p.config < 4) return p.config;
   const long long mt = (p.M + BM - 1) / BM;
   auto tiles = [&](int bn) { return mt * ((p.N + bn - 1) / bn) * p.batch; };
   // largest tile that still gives (nearly) every SM work; small problems take the narrow tile for parallelism
   if (tiles(256) >= g_num_sms) return 2;
+  // just over one wave with 128-wide tiles but exactly fits with 192-wide ones (c_fc: 1024 x 3072 -> 128 tiles)
+  if (tiles(128) > g_num_sms && tiles(192) <= g_num_sms && p.N % 192 == 0) return 3;
   if (tiles(128) * 10 >= (long long)g_num_sms * 6) return 1;
   return tiles(64) > tiles(128) ? 0 : 1;
 }
@@ -563,7 +565,7 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   }
   if (p.M <= 0 || p.N <= 0 || p.batch <= 0) return;
   const int cfg = pick_config(p);
-  const int bn = cfg == 0 ? 64 : (cfg == 1 ? 128 : 256);
+  const int bn = cfg == 0 ? 64 : (cfg == 1 ? 128 : (cfg == 2 ? 256 : 192));
   const int nb2 = p.nbatch2 > 0 ? p.nbatch2 : 1;
   const int nb1 = p.batch / nb2;
   CUtensorMap ta, tb;
@@ -603,7 +605,8 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   }
   if (cfg == 0) launch<64>(ta, tb, td, tx, g, (int)tiles, stream);
   else if (cfg == 1) launch<128>(ta, tb, td, tx, g, (int)tiles, stream);
-  else launch<256>(ta, tb, td, tx, g, (int)tiles, stream);
+  else if (cfg == 2) launch<256>(ta, tb, td, tx, g, (int)tiles, stream);
+  else launch<192>(ta, tb, td, tx, g, (int)tiles, stream);
 }
 
 }  // namespace tds

@@ -3,5 +3,3 @@ cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 echo "== pytest kernels+model"; timeout 900 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_model.py -q -m gpu -x --timeout 120 > gpurun_out/pytest_gpu.log 2>&1; tail -4 gpurun_out/pytest_gpu.log
 echo "== bench ours graph"; timeout 600 python bench.py --steps 100 --warmup 5 > gpurun_out/bench_graph.log 2>&1; tail -1 gpurun_out/bench_graph.log | cut -c1-200
-echo "== bench aux direct / LN two kernels"; TDS_GEMM_AUX_DIRECT=1 TDS_LN_TWO_KERNELS=1 timeout 600 python bench.py --steps 100 --warmup 5 2>&1 | tail -1 | cut -c1-200
-timeout 200 python tools/flash_check.py time 2>&1 | tail -3
