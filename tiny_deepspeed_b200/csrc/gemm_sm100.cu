@@ -24,7 +24,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <mutex>
-#include <unordered_map>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -37,7 +36,6 @@ constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // one 128-byte swizzle row of bf16
 constexpr int UK = 16;        // UMMA K for 16-bit inputs
 constexpr int kThreads = 192;
-constexpr int kEpiWarp0 = 2;
 constexpr uint32_t kStageBufBytes = 4096;   // one 32-row x 64-col bf16 slab, SWIZZLE_128B
 
 enum { EPI_NONE = 0, EPI_GELU_SAVE = 1, EPI_GELU_BWD = 2, EPI_RESIDUAL = 3 };

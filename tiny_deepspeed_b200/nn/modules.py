@@ -11,6 +11,26 @@ from .. import ops
 from .policy import policy_of
 
 
+# Tracing: TDS_NVTX=1 wraps every layer's forward/backward in an NVTX range (visible in nsys / ncu --nvtx);
+# zero overhead when off because the decorator returns the function unchanged.
+_NVTX = os.environ.get("TDS_NVTX", "0") == "1"
+
+
+def _traced(name):
+    def deco(fn):
+        if not _NVTX:
+            return fn
+
+        def wrapped(*a, **k):
+            torch.cuda.nvtx.range_push(name)
+            try:
+                return fn(*a, **k)
+            finally:
+                torch.cuda.nvtx.range_pop()
+        return wrapped
+    return deco
+
+
 def _grad_of(policy, param, compute):
     """Run ``compute(out, accumulate) -> grad`` into the policy's buffer and publish the result."""
     out, acc = policy.grad_out(param)
@@ -61,6 +81,7 @@ def _linear_backward(pol, weight, shape, dy, x, tuner, dx_fn):
 
 class _LinearFn(torch.autograd.Function):
     @staticmethod
+    @_traced("linear.fwd")
     def forward(ctx, x, weight, bias, module, residual):
         pol = policy_of(module)
         w = pol.acquire(weight)
@@ -72,6 +93,7 @@ class _LinearFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_traced("linear.bwd")
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         module = ctx.module
@@ -111,6 +133,7 @@ class _MLPFn(torch.autograd.Function):
     live in GEMM epilogues (EPI_GELU_SAVE on c_fc, EPI_GELU_BWD on c_proj's dX)."""
 
     @staticmethod
+    @_traced("mlp.fwd")
     def forward(ctx, x, fc, proj, residual):
         pf, pp = policy_of(fc), policy_of(proj)
         pre = torch.empty(*x.shape[:-1], fc.out_features, device=x.device, dtype=x.dtype)
@@ -126,6 +149,7 @@ class _MLPFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_traced("mlp.bwd")
     def backward(ctx, dy):
         x, pre, act = ctx.saved_tensors
         fc, proj = ctx.fc, ctx.proj
@@ -166,6 +190,7 @@ def fused_mlp(x, fc: Linear, proj: Linear, residual=None):
 
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
+    @_traced("layernorm.fwd")
     def forward(ctx, x, weight, bias, module, with_residual):
         pol = policy_of(module)
         w, b = pol.acquire(weight), pol.acquire(bias)
@@ -182,6 +207,7 @@ class _LayerNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_traced("layernorm.bwd")
     def backward(ctx, dy, dres=None):
         x, mean, rstd = ctx.saved_tensors
         module = ctx.module
@@ -226,6 +252,7 @@ class LayerNorm(tnn.LayerNorm):
 
 class _EmbeddingFn(torch.autograd.Function):
     @staticmethod
+    @_traced("embedding.fwd")
     def forward(ctx, idx, weight, module, add):
         pol = policy_of(module)
         w = pol.acquire(weight)
@@ -238,6 +265,7 @@ class _EmbeddingFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_traced("embedding.bwd")
     def backward(ctx, dy):
         (idx,) = ctx.saved_tensors
         module = ctx.module
@@ -271,11 +299,13 @@ class Embedding(tnn.Embedding):
 
 class _GeluFn(torch.autograd.Function):
     @staticmethod
+    @_traced("gelu.fwd")
     def forward(ctx, x):
         ctx.save_for_backward(x)
         return ops.gelu_forward(x)
 
     @staticmethod
+    @_traced("gelu.bwd")
     def backward(ctx, dy):
         (x,) = ctx.saved_tensors
         return ops.gelu_backward(dy, x)
@@ -292,6 +322,7 @@ class GELU(tnn.GELU):
 
 class _AttnFn(torch.autograd.Function):
     @staticmethod
+    @_traced("attention.fwd")
     def forward(ctx, qkv, n_head):
         y, aux = ops.causal_attention_forward(qkv, n_head)      # aux: LSE (flash kernels) or P (materialised path)
         ctx.n_head = n_head
@@ -299,6 +330,7 @@ class _AttnFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @_traced("attention.bwd")
     def backward(ctx, dy):
         qkv, aux, y = ctx.saved_tensors
         return ops.causal_attention_backward(dy.contiguous(), qkv, aux, ctx.n_head, y=y), None
@@ -311,12 +343,14 @@ def causal_self_attention(qkv: torch.Tensor, n_head: int) -> torch.Tensor:
 
 class _XentFn(torch.autograd.Function):
     @staticmethod
+    @_traced("cross_entropy.fwd")
     def forward(ctx, logits, targets):
         loss, lse = ops.cross_entropy_forward(logits, targets)
         ctx.save_for_backward(logits, targets, lse)
         return loss.to(torch.float32)
 
     @staticmethod
+    @_traced("cross_entropy.bwd")
     def backward(ctx, g):
         logits, targets, lse = ctx.saved_tensors
         return ops.cross_entropy_backward(g, logits, targets, lse), None

@@ -39,13 +39,6 @@ __all__ = [
 ]
 
 
-def _tuned(tuner, key, funcs, *args, **kw):
-    """Dispatch through a RuntimeAutoTuner when one is supplied (reference ops/linear.py:11-15)."""
-    if tuner is None or len(funcs) == 1:
-        return funcs[0](*args, **kw)
-    return tuner.choose_function(funcs, *args, key=key, **kw)
-
-
 # --------------------------------------------------------------------------------------
 # GEMM
 # --------------------------------------------------------------------------------------
