@@ -273,3 +273,74 @@ def test_flash_attention_kernels(B, T, nh):
     assert P.dtype == torch.bfloat16
     assert (y.float() - y2.float()).norm() / ref.norm() < 8e-3
     assert (dqkv.float() - d2.float()).norm() / qf.grad.norm() < 2e-2
+
+
+# ---- fp32 operands through kind::tf32 (fp32 models; reference trains fp32, example/ddp/train.py:22) ---------------------
+def _rel(got, ref):
+    return ((got.float() - ref.float()).norm() / ref.float().norm()).item()
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])
+@pytest.mark.parametrize("M,N,K", [(256, 384, 512), (1024, 768, 3072), (200, 136, 104), (128, 64, 32)])
+def test_gemm_tf32_layouts(M, N, K, a_mn, b_mn):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(K, M, device=_dev()) if a_mn else torch.randn(M, K, device=_dev())
+    b = torch.randn(K, N, device=_dev()) if b_mn else torch.randn(N, K, device=_dev())
+    A = a.t() if a_mn else a
+    Bm = b.t() if b_mn else b
+    ref = A.double() @ Bm.double().t()
+    got = ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn)
+    assert got.dtype == torch.float32
+    assert _rel(got, ref) < 1e-3, _rel(got, ref)      # TF32: 10-bit mantissa, fp32 accumulate
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+def test_gemm_tf32_configs_epilogues(cfg):
+    torch.manual_seed(cfg)
+    x, w, bias = torch.randn(512, 768, device=_dev()), torch.randn(1536, 768, device=_dev()) * 0.05, torch.randn(1536, device=_dev())
+    lin = (x.double() @ w.double().t() + bias.double()).float()
+    pre = torch.empty(512, 1536, device=_dev())
+    act = ops.gemm(x, w, bias=bias, aux=pre, epi=ops.EPI_GELU_SAVE, config=cfg)
+    assert _rel(pre, lin) < 1e-3
+    assert _rel(act, F.gelu(lin, approximate="tanh")) < 2e-3
+    res = torch.randn(512, 1536, device=_dev())
+    got = ops.gemm(x, w, bias=bias, aux=res, epi=ops.EPI_RESIDUAL, config=cfg)
+    assert _rel(got, lin + res) < 1e-3
+    dy = torch.randn(512, 768, device=_dev())
+    w2 = torch.randn(768, 1536, device=_dev()) * 0.05
+    p = pre.clone().requires_grad_()
+    F.gelu(p, approximate="tanh").backward(dy @ w2)
+    got = ops.gemm(dy, w2, b_mn=True, aux=pre, epi=ops.EPI_GELU_BWD, config=cfg)
+    assert _rel(got, p.grad) < 2e-3
+    acc = torch.ones(512, 1536, device=_dev())
+    ops.gemm(x, w, out=acc, accumulate=True, alpha=0.5, config=cfg)
+    assert _rel(acc, 1 + 0.5 * (lin - bias)) < 1e-3
+    # ragged N / unaligned bias path
+    wr = torch.randn(100, 768, device=_dev()) * 0.05
+    br = torch.randn(100, device=_dev())
+    got = ops.gemm(x, wr, bias=br, config=cfg)
+    assert _rel(got, x @ wr.t() + br) < 1e-3
+
+
+def test_cast_kernel():
+    x = torch.randn(1000, 37, device=_dev())
+    y = ops.cast(x, torch.bfloat16)
+    assert y.dtype == torch.bfloat16 and torch.equal(y, x.to(torch.bfloat16))
+    z = ops.cast(y, torch.float32)
+    assert z.dtype == torch.float32 and torch.equal(z, y.float())
+
+
+def test_attention_fp32_model_dtype():
+    B, T, nh, hs = 2, 256, 4, 64
+    C = nh * hs
+    qkv = (torch.randn(B, T, 3 * C, device=_dev()) * 0.5).requires_grad_()
+    q, k, v = (t.view(B, T, nh, hs).transpose(1, 2) for t in qkv.split(C, dim=2))
+    yr = F.scaled_dot_product_attention(q, k, v, is_causal=True).transpose(1, 2).reshape(B, T, C)
+    dy = torch.randn_like(yr)
+    (gr,) = torch.autograd.grad(yr, qkv, dy)
+    y, P = ops.causal_attention_forward(qkv.detach(), nh)
+    assert y.dtype == torch.float32
+    assert _rel(y, yr) < 1e-2
+    g = ops.causal_attention_backward(dy, qkv.detach(), P, nh, y=y)
+    assert g.dtype == torch.float32
+    assert _rel(g, gr) < 2e-2

@@ -79,3 +79,37 @@ def test_optimizer_in_backward_overlap_matches_plain_step():
     assert l2 == pytest.approx(l1, rel=1e-4, abs=1e-4), (l1, l2)
     for (n, a), (_, b) in zip(m1.named_parameters(), m2.named_parameters()):
         torch.testing.assert_close(a.float(), b.float(), rtol=1e-3, atol=1e-4, msg=n)
+
+
+def test_fp32_model_matches_oracle_and_trains():
+    """fp32 parameters (the reference's dtype, example/single_device/train.py:16): GEMMs run as TF32 on tcgen05, LN / CE /
+    Adam in fp32, the attention core on the bf16 flash kernels."""
+    torch.manual_seed(3)
+    cfg = gpt2_config("tiny", n_layer=2, n_head=4, n_embd=256, vocab_size=2048, block_size=256, bias=True)
+    m = GPT2Model(cfg).to(device="cuda", dtype=torch.float32)
+    x = torch.randint(0, cfg.vocab_size, (2, 256), device="cuda")
+    y = torch.randint(0, cfg.vocab_size, (2, 256), device="cuda")
+    _, loss = m(x, y)
+    loss.backward()
+    got = {n: p.grad.clone() for n, p in m.named_parameters()}
+    assert all(g.dtype == torch.float32 for g in got.values())
+    for p in m.parameters():
+        p.grad = None
+    ops.force_torch(True)
+    try:
+        _, rloss = m(x, y)
+        rloss.backward()
+    finally:
+        ops.force_torch(False)
+    torch.testing.assert_close(loss, rloss, rtol=1e-3, atol=1e-3)
+    for n, p in m.named_parameters():
+        rel = (got[n] - p.grad).norm() / (p.grad.norm() + 1e-12)
+        assert rel < 2e-2, (n, float(rel))
+        p.grad = None
+    # drop the eager autograd graphs: their AccumulateGrad nodes are bound to the default stream and would otherwise be
+    # reused inside the capture (torch's usual "no default-stream autograd state before graph capture" rule)
+    del loss, rloss
+    opt = tds.AdamW(m.named_parameters(), lr=1e-3, weight_decay=0.1)
+    step = tds.TrainStep(m, opt, use_graph=True, warmup=2)
+    losses = [float(step(x, y)) for _ in range(8)]
+    assert losses[-1] < losses[0] - 0.05, losses

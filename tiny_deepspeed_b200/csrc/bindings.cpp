@@ -33,7 +33,7 @@ void check_launch(const char* what) {
 // GEMM
 // ---------------------------------------------------------------------------------------------------
 GemmOperand operand(const Tensor& t, bool mn, int64_t& rows_out, int64_t& k_out, int64_t& nb1, int64_t& nb2) {
-  TORCH_CHECK(t.scalar_type() == at::kBFloat16, "gemm operands must be bf16");
+  TORCH_CHECK(t.scalar_type() == at::kBFloat16 || t.scalar_type() == at::kFloat, "gemm operands must be bf16 or fp32 (TF32 MMA)");
   TORCH_CHECK(t.dim() >= 2 && t.dim() <= 4, "gemm operand rank must be 2..4");
   TORCH_CHECK(t.stride(-1) == 1, "gemm operand inner stride must be 1");
   GemmOperand op{};
@@ -47,9 +47,10 @@ GemmOperand operand(const Tensor& t, bool mn, int64_t& rows_out, int64_t& k_out,
   op.batch_stride = 0; op.batch_stride2 = 0;
   if (t.dim() == 3) { nb1 = t.size(0); op.batch_stride = t.stride(0); }
   if (t.dim() == 4) { nb1 = t.size(0); nb2 = t.size(1); op.batch_stride = t.stride(0); op.batch_stride2 = t.stride(1); }
-  TORCH_CHECK(op.ld % 8 == 0 && (reinterpret_cast<uintptr_t>(op.ptr) % 16) == 0 && op.batch_stride % 8 == 0 &&
-                  op.batch_stride2 % 8 == 0,
-              "gemm operand must be 16-byte aligned with row/batch strides multiple of 8 elements (TMA)");
+  const int64_t al = t.scalar_type() == at::kFloat ? 4 : 8;   // elements per 16 bytes
+  TORCH_CHECK(op.ld % al == 0 && (reinterpret_cast<uintptr_t>(op.ptr) % 16) == 0 && op.batch_stride % al == 0 &&
+                  op.batch_stride2 % al == 0,
+              "gemm operand must be 16-byte aligned with row/batch strides multiple of 16 bytes (TMA)");
   return op;
 }
 
@@ -62,6 +63,9 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, con
   int64_t M, K, N, K2, a1, a2, b1, b2;
   p.a = operand(a, a_mn, M, K, a1, a2);
   p.b = operand(b, b_mn, N, K2, b1, b2);
+  TORCH_CHECK(a.scalar_type() == b.scalar_type(), "gemm: operand dtypes differ");
+  p.in_dtype = dtype_of(a);
+  p.io_dtype = kBF16;
   TORCH_CHECK(K == K2, "gemm: reduction dims differ: ", K, " vs ", K2);
   TORCH_CHECK(a1 == b1 && a2 == b2, "gemm: batch dims differ");
   TORCH_CHECK(K > 0, "gemm: empty reduction dim");
@@ -72,13 +76,15 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, con
   if (d.dim() == 4) { TORCH_CHECK(d.size(0) == a1 && d.size(1) == a2); p.d_batch_stride = d.stride(0); p.d_batch_stride2 = d.stride(1); }
   p.bias = nullptr;
   if (bias.has_value() && bias->defined()) {
-    TORCH_CHECK(bias->scalar_type() == at::kBFloat16 && bias->numel() == N && bias->is_contiguous(), "gemm: bias must be bf16 [N]");
+    TORCH_CHECK(bias->numel() == N && bias->is_contiguous(), "gemm: bias must be a contiguous [N]");
+    p.io_dtype = dtype_of(*bias);
     p.bias = bias->data_ptr();
   }
   p.aux = nullptr; p.ld_aux = 0;
   if (aux.has_value() && aux->defined()) {
-    TORCH_CHECK(aux->scalar_type() == at::kBFloat16 && aux->dim() == 2 && aux->size(0) == M && aux->size(1) == N &&
-                    aux->stride(1) == 1, "gemm: aux must be bf16 [M,N]");
+    TORCH_CHECK(aux->dim() == 2 && aux->size(0) == M && aux->size(1) == N && aux->stride(1) == 1, "gemm: aux must be [M,N]");
+    TORCH_CHECK(!p.bias || dtype_of(*aux) == p.io_dtype, "gemm: bias and aux dtypes differ");
+    p.io_dtype = dtype_of(*aux);
     TORCH_CHECK(a1 * a2 == 1, "gemm: aux epilogues are not batched");
     p.aux = aux->data_ptr(); p.ld_aux = aux->stride(0);
   }
@@ -210,6 +216,16 @@ Tensor gelu_bwd_(const Tensor& dy, const Tensor& x) {
   gelu_bwd(dy.data_ptr(), x.data_ptr(), dx.data_ptr(), x.numel(), dtype_of(x), cur_stream());
   check_launch("gelu_bwd");
   return dx;
+}
+Tensor cast_(const Tensor& x) {
+  check_cuda(x, "x");
+  TORCH_CHECK(x.is_contiguous(), "cast: input must be contiguous");
+  c10::cuda::CUDAGuard guard(x.device());
+  const int dt = dtype_of(x);
+  Tensor y = torch::empty(x.sizes(), x.options().dtype(dt == kBF16 ? at::kFloat : at::kBFloat16));
+  cast(x.data_ptr(), dt, y.data_ptr(), x.numel(), cur_stream());
+  check_launch("cast");
+  return y;
 }
 void colsum_(const Tensor& x, Tensor& out, bool accumulate) {
   check_cuda(x, "x");
@@ -347,6 +363,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("cross_entropy_bwd", &cross_entropy_bwd_);
   m.def("gelu_fwd", &gelu_fwd_);
   m.def("gelu_bwd", &gelu_bwd_);
+  m.def("cast", &cast_);
   m.def("colsum", &colsum_);
   m.def("sum_slices", &sum_slices_);
   m.def("flash_fwd", &flash_fwd_);

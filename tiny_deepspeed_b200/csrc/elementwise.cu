@@ -475,6 +475,26 @@ void gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, cud
   TDS_DISPATCH(dtype, (launch_k(gelu_kernel<T, true>, dim3(ew_grid(n)), dim3(256), 0, s, (const T*)dy, (const T*)x, (T*)dx, n)));
 }
 
+// dtype conversion bf16 <-> fp32 (fp32 models run their attention core on the bf16 flash kernels)
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ x, TO* __restrict__ out, int64_t n) {
+  pdl_launch(); pdl_wait();
+  const int64_t nvec = n >> 3;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    float v[8];
+    V8<TI>::ld(x + i * 8, v);
+    V8<TO>::st(out + i * 8, v);
+  }
+  if (blockIdx.x == 0)
+    for (int64_t i = (nvec << 3) + threadIdx.x; i < n; i += blockDim.x) stf(out + i, ldf(x + i));
+}
+void cast(const void* x, int in_dtype, void* out, int64_t n, cudaStream_t s) {
+  if (in_dtype == kBF16)
+    launch_k(cast_kernel<__nv_bfloat16, float>, dim3(ew_grid(n)), dim3(256), 0, s, (const __nv_bfloat16*)x, (float*)out, n);
+  else
+    launch_k(cast_kernel<float, __nv_bfloat16>, dim3(ew_grid(n)), dim3(256), 0, s, (const float*)x, (__nv_bfloat16*)out, n);
+}
+
 // out[n] (+)= sum_m x[m][n]; CTA = 32 columns x 8 row-lanes, rows strided, then smem fold
 template <typename T>
 __global__ void colsum_kernel(const T* __restrict__ x, T* __restrict__ out, int M, int N, int accumulate) {

@@ -1,4 +1,5 @@
-// Persistent warp-specialised tcgen05 GEMM for sm_100a (bf16 x bf16 -> fp32 in TMEM -> bf16/fp32).
+// Persistent warp-specialised tcgen05 GEMM for sm_100a (bf16 x bf16 -> fp32 in TMEM -> bf16/fp32, and fp32 x fp32 consumed as
+// TF32 by kind::tf32 -> fp32 for fp32 models: same 128-byte-row smem layout, 32 instead of 64 K elements per stage).
 //
 //   D[b][m][n] = alpha * sum_k A(b,m,k) * B(b,n,k)      A: [M,K] K-major or [K,M] MN-major, same for B
 //
@@ -42,8 +43,9 @@ enum { EPI_NONE = 0, EPI_GELU_SAVE = 1, EPI_GELU_BWD = 2, EPI_RESIDUAL = 3 };
 
 struct GemmDev {
   void* d; int d_f32; long long ldd, dbs1, dbs2;
-  const __nv_bfloat16* bias;
-  __nv_bfloat16* aux; long long ld_aux;
+  const void* bias;       // [N], bf16 (fp32 when io_f32)
+  void* aux; long long ld_aux;   // [M,N], bf16 (fp32 when io_f32)
+  int io_f32;     // bias / aux are fp32 (fp32 model)
   int epi, accumulate; float alpha;
   int M, N, K, batch, nb2;
   int a_mn, b_mn;
@@ -63,18 +65,36 @@ template <int BN> struct Cfg {
   static constexpr int kTmemCols = BN == 64 ? 128 : (BN == 128 ? 256 : 512);   // power of two >= 2 * BN
 };
 
+template <int KB>
 __device__ __forceinline__ void tile_k_range(const GemmDev& g, int m0, int nkb, int& kb0, int& kb1) {
   kb0 = 0; kb1 = nkb;
-  if (g.tri == 2) { int e = (m0 + BM + BK - 1) / BK; kb1 = e < nkb ? e : nkb; }
-  else if (g.tri == 3) { kb0 = m0 / BK; }
+  if (g.tri == 2) { int e = (m0 + BM + KB - 1) / KB; kb1 = e < nkb ? e : nkb; }
+  else if (g.tri == 3) { kb0 = m0 / KB; }
 }
 
-template <int BN>
+// 8 consecutive elements of a bf16 or fp32 array as floats / back (epilogue operands of either model dtype)
+__device__ __forceinline__ void ld8_any(const void* base, long long idx, int f32, float (&out)[8]) {
+  if (f32) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(base) + idx);
+    const float4 a = p[0], b = p[1];
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w; out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  } else {
+    unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(base) + idx), out);
+  }
+}
+__device__ __forceinline__ float ld1_any(const void* base, long long idx, int f32) {
+  return f32 ? reinterpret_cast<const float*>(base)[idx] : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[idx]);
+}
+
+// F32 = fp32 operands (kind::tf32): compile-time so the bf16 instantiation keeps its fully unrolled producer / issue loops
+template <int BN, bool F32>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
             const __grid_constant__ GemmDev g) {
   using C = Cfg<BN>;
+  constexpr int kBK = F32 ? 32 : BK;     // K elements per stage = one 128-byte row
+  constexpr int kGrp = F32 ? 32 : 64;    // MN elements per 128-byte row of an MN-major operand
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
@@ -123,7 +143,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int n_tiles = (g.N + BN - 1) / BN;
   const int tiles_per_batch = m_tiles * n_tiles;
   const int total_tiles = tiles_per_batch * g.batch;
-  const int nkb = (g.K + BK - 1) / BK;
+  const int nkb = (g.K + kBK - 1) / kBK;
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -134,28 +154,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int m0 = (r % m_tiles) * BM, n0 = (r / m_tiles) * BN;   // m fastest: neighbours share the B tile in L2
         if (g.tri == 1 && n0 > m0 + BM - 1) continue;
         const int b1 = b / g.nb2, b2 = b % g.nb2;
-        int kb0, kb1; tile_k_range(g, m0, nkb, kb0, kb1);
+        int kb0, kb1; tile_k_range<kBK>(g, m0, nkb, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           ptx::mbar_expect_tx(full_bar(stage), C::kABytes + C::kBBytes);
           const uint32_t a_dst = sA + stage * C::kABytes, b_dst = sB + stage * C::kBBytes;
-          const int k0 = kb * BK;
+          const int k0 = kb * kBK;
+          // MN-major operands arrive as one box per 128-byte-wide MN group (64 bf16 / 32 fp32), bk k-rows each
+          constexpr uint32_t grp_bytes = (uint32_t)kBK * 128u;
           if (!g.a_mn) {
             ptx::tma_load_4d(a_dst, &tma_a, full_bar(stage), k0, m0, b2, b1);
           } else {
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i)
-              ptx::tma_load_4d(a_dst + i * (BK * 128), &tma_a, full_bar(stage), m0 + 64 * i, k0, b2, b1);
+            for (int i = 0; i < BM / kGrp; ++i)
+              ptx::tma_load_4d(a_dst + i * grp_bytes, &tma_a, full_bar(stage), m0 + kGrp * i, k0, b2, b1);
           }
           if (g.cm == 1) {
             if (!g.b_mn) {
               ptx::tma_load_4d(b_dst, &tma_b, full_bar(stage), k0, n0, b2, b1);
             } else {
 #pragma unroll
-              for (int i = 0; i < BN / 64; ++i)
-                ptx::tma_load_4d(b_dst + i * (BK * 128), &tma_b, full_bar(stage), n0 + 64 * i, k0, b2, b1);
+              for (int i = 0; i < BN / kGrp; ++i)
+                ptx::tma_load_4d(b_dst + i * grp_bytes, &tma_b, full_bar(stage), n0 + kGrp * i, k0, b2, b1);
             }
-          } else {
+          } else {   // (bf16 only: pick_cluster never forms clusters for fp32 operands)
             // The cm CTAs of the cluster work on cm consecutive M tiles of the SAME N tile: each fetches 1/cm of
             // the B tile and the TMA multicasts it into every CTA's smem (one L2 / NVLink read per cluster).
             if (!g.b_mn) {
@@ -180,13 +202,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int local = 0;
     // descriptor strides: K-major: SBO = 1024 (8 rows x 128 B), per-UMMA_K advance 32 B;
     //                     MN-major: LBO = BK*128 (next 64-wide MN group), SBO = 1024, advance 16 k-rows = 2048 B
-    const uint32_t a_lbo = g.a_mn ? BK * 128 : 16, b_lbo = g.b_mn ? BK * 128 : 16;
-    const uint32_t a_adv = g.a_mn ? UK * 128 : UK * 2, b_adv = g.b_mn ? UK * 128 : UK * 2;
+    //                     (fp32/TF32: UMMA K = 8 -> 32 B per k-step K-major as well, 8 k-rows = 1024 B MN-major)
+    constexpr uint32_t uk_rows = F32 ? 8u : (uint32_t)UK;
+    const uint32_t a_lbo = g.a_mn ? kBK * 128 : 16, b_lbo = g.b_mn ? kBK * 128 : 16;
+    const uint32_t a_adv = g.a_mn ? uk_rows * 128 : 32, b_adv = g.b_mn ? uk_rows * 128 : 32;
+    // MN-major fp32 operands sit in the 32-byte-atom swizzle (the only MN-major layout kind::tf32 accepts)
+    const uint32_t a_lt = (F32 && g.a_mn) ? 1u : 2u, b_lt = (F32 && g.b_mn) ? 1u : 2u;
+    const uint32_t a_sbo = a_lt == 1u ? 512u : 1024u, b_sbo = b_lt == 1u ? 512u : 1024u;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int r = t % tiles_per_batch;
       const int m0 = (r % m_tiles) * BM, n0 = (r / m_tiles) * BN;
       if (g.tri == 1 && n0 > m0 + BM - 1) continue;
-      int kb0, kb1; tile_k_range(g, m0, nkb, kb0, kb1);
+      int kb0, kb1; tile_k_range<kBK>(g, m0, nkb, kb0, kb1);
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       ++local;
@@ -200,9 +227,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           const uint32_t a_s = sA + stage * C::kABytes, b_s = sB + stage * C::kBBytes;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
-            const uint64_t da = ptx::make_smem_desc(a_s + k * a_adv, a_lbo, 1024);
-            const uint64_t db = ptx::make_smem_desc(b_s + k * b_adv, b_lbo, 1024);
-            if (!(g.dbg & 2)) ptx::mma_f16_ss(d_tmem, da, db, g.idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            const uint64_t da = ptx::make_smem_desc(a_s + k * a_adv, a_lbo, a_sbo, a_lt);
+            const uint64_t db = ptx::make_smem_desc(b_s + k * b_adv, b_lbo, b_sbo, b_lt);
+            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            if (F32) ptx::mma_tf32_ss(d_tmem, da, db, g.idesc, acc);
+            else if (!(g.dbg & 2)) ptx::mma_f16_ss(d_tmem, da, db, g.idesc, acc);
           }
           // smem stage reusable once these MMAs retire (told to every CTA of the cluster when B is multicast)
           if (g.cm == 1) ptx::mma_commit(empty_bar(stage));
@@ -272,7 +301,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               const int nc = nb + j8 * 8;
               const bool col_ok = nc + 8 <= g.N;       // N % 8 == 0 on this path
               if (g.bias && col_ok) {
-                float bf[8]; unpack8(ld8(g.bias + nc), bf);
+                float bf[8]; unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(g.bias) + nc), bf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += bf[j];
               }
@@ -288,7 +317,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
                 for (int j = 0; j < 8; ++j) af[j] = 0.f;
                 if (aux_in) unpack8(ptx::ld_shared_16<bf16x8>(abuf + chunk), af);     // OOB rows/cols were zero-filled
-                else if (row_ok && col_ok) unpack8(ld8(g.aux + (long long)m * g.ld_aux + nc), af);
+                else if (row_ok && col_ok) unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(g.aux) + (long long)m * g.ld_aux + nc), af);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                   v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
@@ -320,24 +349,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               if (g.bias) {
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
-                  float bf[8]; unpack8(ld8(g.bias + nb + j8 * 8), bf);
+                  float bf[8]; ld8_any(g.bias, nb + j8 * 8, g.io_f32, bf);
 #pragma unroll
                   for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += bf[j];
                 }
               }
               if (g.epi != EPI_NONE) {
-                __nv_bfloat16* ap = g.aux + (long long)m * g.ld_aux + nb;
+                const long long a_off = (long long)m * g.ld_aux + nb;
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                   float af[8];
                   if (g.epi == EPI_GELU_SAVE) {
-                    bf16x8 pk = pack8(&v[j8 * 8]);
-                    st8(ap + j8 * 8, pk);
-                    unpack8(pk, af);
+                    if (g.io_f32) {
+                      float4* ap = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.aux) + a_off + j8 * 8);
+                      ap[0] = make_float4(v[j8 * 8], v[j8 * 8 + 1], v[j8 * 8 + 2], v[j8 * 8 + 3]);
+                      ap[1] = make_float4(v[j8 * 8 + 4], v[j8 * 8 + 5], v[j8 * 8 + 6], v[j8 * 8 + 7]);
+#pragma unroll
+                      for (int j = 0; j < 8; ++j) af[j] = v[j8 * 8 + j];
+                    } else {
+                      bf16x8 pk = pack8(&v[j8 * 8]);
+                      st8(reinterpret_cast<__nv_bfloat16*>(g.aux) + a_off + j8 * 8, pk);
+                      unpack8(pk, af);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j8 * 8 + j] = gelu_tanh(af[j]);
                   } else {
-                    unpack8(ld8(ap + j8 * 8), af);
+                    ld8_any(g.aux, a_off + j8 * 8, g.io_f32, af);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                       v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
@@ -371,15 +408,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 const int n = nb + j;
                 if (n < g.N) {
                   float x = v[j];
-                  if (g.bias) x += __bfloat162float(g.bias[n]);
+                  if (g.bias) x += ld1_any(g.bias, n, g.io_f32);
+                  const long long ai = (long long)m * g.ld_aux + n;
                   if (g.epi == EPI_GELU_SAVE) {
-                    __nv_bfloat16 pre = __float2bfloat16_rn(x);
-                    g.aux[(long long)m * g.ld_aux + n] = pre;
-                    x = gelu_tanh(__bfloat162float(pre));
+                    if (g.io_f32) {
+                      reinterpret_cast<float*>(g.aux)[ai] = x;
+                    } else {
+                      __nv_bfloat16 pre = __float2bfloat16_rn(x);
+                      reinterpret_cast<__nv_bfloat16*>(g.aux)[ai] = pre;
+                      x = __bfloat162float(pre);
+                    }
+                    x = gelu_tanh(x);
                   } else if (g.epi == EPI_GELU_BWD) {
-                    x *= gelu_tanh_grad(__bfloat162float(g.aux[(long long)m * g.ld_aux + n]));
+                    x *= gelu_tanh_grad(ld1_any(g.aux, ai, g.io_f32));
                   } else if (g.epi == EPI_RESIDUAL) {
-                    x += __bfloat162float(g.aux[(long long)m * g.ld_aux + n]);
+                    x += ld1_any(g.aux, ai, g.io_f32);
                   }
                   if (g.d_f32) {
                     float* dp = reinterpret_cast<float*>(g.d) + d_off + n;
@@ -434,24 +477,32 @@ static EncodeTiledFn get_encode() {
 
 // 4-D map over one bf16 operand: dims (inner, rows, nb2, nb1)
 bool make_map(CUtensorMap* out, const GemmOperand& op, int rows_mn, int K, int nb1, int nb2, int box_rows_kmajor,
-              int box_krows_mnmajor) {
+              int box_krows_mnmajor, bool f32) {
   EncodeTiledFn enc = get_encode();
   if (!enc) return false;
   cuuint64_t dims[4];
   cuuint32_t box[4];
-  if (!op.mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows_mn; box[0] = BK; box[1] = (cuuint32_t)box_rows_kmajor; }
-  else              { dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K; box[0] = 64; box[1] = (cuuint32_t)box_krows_mnmajor; }
+  const cuuint32_t inner = f32 ? 32 : 64;     // one 128-byte swizzle row
+  const cuuint64_t es = f32 ? 4 : 2;
+  if (!op.mn_major) { dims[0] = (cuuint64_t)K; dims[1] = (cuuint64_t)rows_mn; box[0] = inner; box[1] = (cuuint32_t)box_rows_kmajor; }
+  else              { dims[0] = (cuuint64_t)rows_mn; dims[1] = (cuuint64_t)K; box[0] = inner; box[1] = (cuuint32_t)box_krows_mnmajor; }
   dims[2] = (cuuint64_t)nb2; dims[3] = (cuuint64_t)nb1;
   box[2] = 1; box[3] = 1;
-  const cuuint64_t row_bytes = (cuuint64_t)op.ld * 2;
+  const cuuint64_t row_bytes = (cuuint64_t)op.ld * es;
   cuuint64_t strides[3];
   strides[0] = row_bytes;
-  strides[1] = nb2 > 1 ? (cuuint64_t)op.batch_stride2 * 2 : row_bytes * dims[1];
-  strides[2] = nb1 > 1 ? (cuuint64_t)op.batch_stride * 2 : strides[1] * (nb2 > 1 ? (cuuint64_t)nb2 : 1);
+  strides[1] = nb2 > 1 ? (cuuint64_t)op.batch_stride2 * es : row_bytes * dims[1];
+  strides[2] = nb1 > 1 ? (cuuint64_t)op.batch_stride * es : strides[1] * (nb2 > 1 ? (cuuint64_t)nb2 : 1);
   for (int i = 1; i < 3; ++i) if (strides[i] == 0) strides[i] = row_bytes;
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+  // TFLOAT32: the TMA rounds fp32 to TF32 on the way into smem (the MMA would otherwise truncate the low mantissa bits);
+  // TDS_GEMM_TF32_MAP=0 loads the raw fp32 bits instead
+  static const int tf32_map = getenv("TDS_GEMM_TF32_MAP") ? atoi(getenv("TDS_GEMM_TF32_MAP")) : 1;
+  const CUtensorMapDataType dt = !f32 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
+                                      : (tf32_map ? CU_TENSOR_MAP_DATA_TYPE_TFLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32);
+  const CUtensorMapSwizzle sw = (f32 && op.mn_major) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = enc(out, dt, 4, const_cast<void*>(op.ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "[tds] cuTensorMapEncodeTiled failed (%d): dims=(%llu,%llu,%llu,%llu) strides=(%llu,%llu,%llu) ptr=%p\n",
@@ -506,22 +557,22 @@ static int max_clusters(int cm) {
   at[0].val.clusterDim.x = cm; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
   cache[cm] = n;
   return n;
 }
 
-template <int BN>
+template <int BN, bool F32>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                    const GemmDev& g, int tiles, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+    cudaFuncSetAttribute(gemm_kernel<BN, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
     attr_done = true;
   }
   if (g.cm == 1) {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    launch_k(gemm_kernel<BN>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
+    launch_k(gemm_kernel<BN, F32>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
     return;
   }
   // cluster launch: cm consecutive CTAs = cm consecutive M tiles of one N tile; grid is a whole number of clusters
@@ -539,7 +590,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, gemm_kernel<BN>, ta, tb, td, tx, g);
+  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32>, ta, tb, td, tx, g);
 }
 
 // cluster size along M: B-tile multicast divides L2->SM (or NVLink, for a ZeRO-3 peer weight) operand traffic by cm
@@ -548,7 +599,7 @@ static int pick_cluster(const GemmParams& p, int bn) {
   // measured on B200 (profiles/r1_gemm_cluster_sweep.md): at M = 1024 the GPT-2 GEMMs are latency-, not L2-bound, and
   // cluster launch costs more than the multicast saves -> off unless requested
   int want = p.cluster_m > 0 ? p.cluster_m : (env >= 0 ? env : 1);
-  if (want <= 1 || p.tri != 0 || p.batch != 1) return 1;
+  if (want <= 1 || p.tri != 0 || p.batch != 1 || p.in_dtype == kF32) return 1;
   const int m_tiles = (p.M + BM - 1) / BM;
   int cm = 8;
   while (cm > 1 && (cm > want || m_tiles % cm != 0 || (bn / cm) % 8 != 0)) cm >>= 1;
@@ -568,20 +619,23 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   const int nb1 = p.batch / nb2;
   CUtensorMap ta, tb;
   const int cm = pick_cluster(p, bn);
-  if (!make_map(&ta, p.a, p.M, p.K, nb1, nb2, BM) || !make_map(&tb, p.b, p.N, p.K, nb1, nb2, bn / cm, BK / cm)) {
+  const bool f32 = p.in_dtype == kF32;
+  const int bk = f32 ? 32 : BK;
+  if (!make_map(&ta, p.a, p.M, p.K, nb1, nb2, BM, bk, f32) || !make_map(&tb, p.b, p.N, p.K, nb1, nb2, bn / cm, bk / cm, f32)) {
     fprintf(stderr, "[tds] gemm: tensor map creation failed (M=%d N=%d K=%d)\n", p.M, p.N, p.K);
     abort();
   }
   GemmDev g;
   g.d = p.d; g.d_f32 = p.d_dtype == kF32; g.ldd = p.ldd; g.dbs1 = p.d_batch_stride; g.dbs2 = p.d_batch_stride2;
-  g.bias = reinterpret_cast<const __nv_bfloat16*>(p.bias);
-  g.aux = reinterpret_cast<__nv_bfloat16*>(p.aux); g.ld_aux = p.ld_aux;
+  g.bias = p.bias;
+  g.aux = p.aux; g.ld_aux = p.ld_aux;
+  g.io_f32 = p.io_dtype == kF32 ? 1 : 0;
   g.epi = p.aux ? p.epi : EPI_NONE; g.accumulate = p.accumulate ? 1 : 0; g.alpha = p.alpha;
   g.M = p.M; g.N = p.N; g.K = p.K; g.batch = p.batch; g.nb2 = nb2;
   g.a_mn = p.a.mn_major; g.b_mn = p.b.mn_major; g.tri = p.tri;
   static const int dbg_env = getenv("TDS_GEMM_DBG") ? atoi(getenv("TDS_GEMM_DBG")) : 0;
   g.dbg = dbg_env;
-  g.idesc = make_idesc_bf16(BM, bn, p.a.mn_major, p.b.mn_major);
+  g.idesc = f32 ? make_idesc_tf32(BM, bn, p.a.mn_major, p.b.mn_major) : make_idesc_bf16(BM, bn, p.a.mn_major, p.b.mn_major);
   g.cm = cm;
   const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.batch;
   // output through TMA (coalesced 128-byte rows) whenever the layout allows it
@@ -590,7 +644,7 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   static const int no_tma_store = getenv("TDS_GEMM_DIRECT_STORE") ? atoi(getenv("TDS_GEMM_DIRECT_STORE")) : 0;
   const bool aligned = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) && (p.N % 8 == 0) &&
                        (p.d_batch_stride % 8 == 0) && (p.d_batch_stride2 % 8 == 0);
-  if (!no_tma_store && p.d_dtype == kBF16 && !p.accumulate && aligned) {
+  if (!no_tma_store && p.d_dtype == kBF16 && !p.accumulate && aligned && !g.io_f32) {
     GemmOperand od{p.d, p.ldd, p.d_batch_stride, p.d_batch_stride2, false};
     bool ok = make_map(&td, od, p.M, p.N, nb1, nb2, 32);
     if (ok && g.epi != EPI_NONE) {
@@ -601,10 +655,17 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
     }
     g.tma_store = ok ? 1 : 0;
   }
-  if (cfg == 0) launch<64>(ta, tb, td, tx, g, (int)tiles, stream);
-  else if (cfg == 1) launch<128>(ta, tb, td, tx, g, (int)tiles, stream);
-  else if (cfg == 2) launch<256>(ta, tb, td, tx, g, (int)tiles, stream);
-  else launch<192>(ta, tb, td, tx, g, (int)tiles, stream);
+  if (f32) {
+    if (cfg == 0) launch<64, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    else if (cfg == 1) launch<128, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    else if (cfg == 2) launch<256, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    else launch<192, true>(ta, tb, td, tx, g, (int)tiles, stream);
+  } else {
+    if (cfg == 0) launch<64, false>(ta, tb, td, tx, g, (int)tiles, stream);
+    else if (cfg == 1) launch<128, false>(ta, tb, td, tx, g, (int)tiles, stream);
+    else if (cfg == 2) launch<256, false>(ta, tb, td, tx, g, (int)tiles, stream);
+    else launch<192, false>(ta, tb, td, tx, g, (int)tiles, stream);
+  }
 }
 
 }  // namespace tds

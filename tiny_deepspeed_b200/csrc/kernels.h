@@ -8,7 +8,7 @@ namespace tds {
 enum DType : int { kBF16 = 0, kF32 = 1 };
 
 // ---- GEMM (gemm_sm100.cu) ---------------------------------------------------------------------
-// D[b][m][n] = alpha * sum_k A(b,m,k) * B(b,n,k)  (+ epilogue).  bf16 operands, fp32 accumulate in TMEM.
+// D[b][m][n] = alpha * sum_k A(b,m,k) * B(b,n,k)  (+ epilogue).  bf16 (or fp32-as-TF32) operands, fp32 accumulate in TMEM.
 struct GemmOperand {
   const void* ptr;      // bf16
   int64_t ld;           // elements between consecutive rows of the stored 2-D matrix
@@ -19,8 +19,10 @@ struct GemmOperand {
 struct GemmParams {
   GemmOperand a, b;
   void* d;  int d_dtype;  int64_t ldd, d_batch_stride, d_batch_stride2;
-  const void* bias;       // [N] bf16 or nullptr
-  void* aux;  int64_t ld_aux;   // bf16 [M,N] (no batch) or nullptr
+  int in_dtype;           // kBF16: bf16 operands (kind::f16); kF32: fp32 operands consumed as TF32 (kind::tf32)
+  int io_dtype;           // dtype of bias / aux (kBF16 or kF32)
+  const void* bias;       // [N] or nullptr
+  void* aux;  int64_t ld_aux;   // [M,N] (no batch) or nullptr
   int epi;                // EPI_* (see ops/__init__.py)
   bool accumulate;        // D += result
   float alpha;
@@ -52,6 +54,7 @@ void xent_bwd(const void* logits, const int64_t* tgt, const float* lse, const fl
               int M, int V, int dtype, cudaStream_t s);
 void gelu_fwd(const void* x, void* y, int64_t n, int dtype, cudaStream_t s);
 void gelu_bwd(const void* dy, const void* x, void* dx, int64_t n, int dtype, cudaStream_t s);
+void cast(const void* x, int in_dtype, void* out, int64_t n, cudaStream_t s);   // bf16 <-> fp32 (out is the other dtype)
 void colsum(const void* x, void* out, bool accumulate, int M, int N, int dtype, cudaStream_t s);
 void sum_slices(const float* ws, void* out_bf16, int64_t n, int S, cudaStream_t s);   // split-K fold (fast_rows.cu)
 

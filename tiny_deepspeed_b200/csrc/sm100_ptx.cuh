@@ -122,6 +122,15 @@ TDS_PTX void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint3
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// fp32 operands consumed as TF32 (10-bit mantissa), UMMA K = 8, fp32 accumulate.
+TDS_PTX void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // All previously issued tcgen05.mma of this thread arrive on the mbarrier when they complete.
 TDS_PTX void mma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -153,13 +162,15 @@ TDS_PTX void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: 
 //   K-major  tile [rows][64 x bf16]: 8-row groups are 1024 B apart  -> SBO = 1024, LBO unused.
 //   MN-major tile [k rows][64 x bf16] per 64-wide MN group: 8-k-row groups 1024 B apart -> SBO = 1024,
 //            consecutive 64-wide MN groups LBO bytes apart.
-TDS_PTX uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+//   MN-major fp32 (TF32) tile: the only legal layout is SWIZZLE_128B_BASE32B (layout type 1: 32-byte chunks XOR-ed with the
+//            k-row index mod 4, = TMA CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): 4-k-row groups 512 B apart -> SBO = 512.
+TDS_PTX uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type = 2) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
   d |= 1ull << 46;   // descriptor version (sm_100)
-  d |= 2ull << 61;   // SWIZZLE_128B
+  d |= static_cast<uint64_t>(layout_type) << 61;   // 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B
   return d;
 }
 
@@ -173,6 +184,19 @@ __host__ __device__ inline uint32_t make_idesc_bf16(int M, int N, bool a_mn, boo
   d |= 1u << 10;                     // b_format  = BF16
   d |= (a_mn ? 1u : 0u) << 15;       // a_major   (0 = K-major, 1 = MN-major)
   d |= (b_mn ? 1u : 0u) << 16;       // b_major
+  d |= static_cast<uint32_t>(N >> 3) << 17;
+  d |= static_cast<uint32_t>(M >> 4) << 24;
+  return d;
+}
+
+// Instruction descriptor for kind::tf32 (fp32 storage read as TF32) with fp32 accumulate.
+__host__ __device__ inline uint32_t make_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  uint32_t d = 0;
+  d |= 1u << 4;                      // c_format  = F32
+  d |= 2u << 7;                      // a_format  = TF32
+  d |= 2u << 10;                     // b_format  = TF32
+  d |= (a_mn ? 1u : 0u) << 15;
+  d |= (b_mn ? 1u : 0u) << 16;
   d |= static_cast<uint32_t>(N >> 3) << 17;
   d |= static_cast<uint32_t>(M >> 4) << 24;
   return d;

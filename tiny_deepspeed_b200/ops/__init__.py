@@ -180,7 +180,7 @@ def linear_input_grad(grad_output, weight, runtime_tuner=None, *, gelu_aux=None)
     dy2 = _flat2d(grad_output)
     if gelu_aux is not None:
         dx = gemm(dy2, weight, b_mn=True, aux=_flat2d(gelu_aux), epi=EPI_GELU_BWD)
-    elif on_gpu(dy2) and weight.shape[0] >= 8192 and _splitk_factor(dy2.shape[0], weight.shape[1], weight.shape[0]) > 1:
+    elif on_gpu(dy2) and dy2.dtype == torch.bfloat16 and weight.shape[0] >= 8192 and _splitk_factor(dy2.shape[0], weight.shape[1], weight.shape[0]) > 1:
         dx = gemm_splitk(dy2, weight, _splitk_factor(dy2.shape[0], weight.shape[1], weight.shape[0]))
     else:
         dx = _gemm_tuned(runtime_tuner, "linear_dx", dy2, weight, b_mn=True)
@@ -365,6 +365,17 @@ def set_flash(flag: bool) -> None:
     _flash = bool(flag)
 
 
+def cast(x, dtype):
+    """bf16 <-> fp32 conversion (one kernel of ours on GPU)."""
+    if x.dtype == dtype:
+        return x
+    if on_gpu(x) and {x.dtype, dtype} == {torch.float32, torch.bfloat16}:
+        y = ext().cast(x.contiguous())
+        count_launch()
+        return y
+    return x.to(dtype)
+
+
 def _split_heads(qkv, n_head):
     B, T, C3 = qkv.shape
     C = C3 // 3
@@ -379,6 +390,10 @@ def causal_attention_forward(qkv, n_head):
     probabilities ``P [B,nh,T,T]`` kept for backward.  GPU: two batched tcgen05 GEMMs (strided
     head views, no transposes) + one causal-softmax kernel.  Replaces the reference's
     ``standard_attention`` (example/model.py:29-42)."""
+    if on_gpu(qkv) and qkv.dtype == torch.float32:
+        # fp32 model: the attention core runs on the bf16 tensor-core kernels (fp32 softmax statistics / accumulation)
+        y, P = causal_attention_forward(cast(qkv, torch.bfloat16), n_head)
+        return cast(y, torch.float32), P
     B, T, C3 = qkv.shape
     C = C3 // 3
     hs = C // n_head
@@ -409,6 +424,11 @@ def causal_attention_backward(grad_y, qkv, P, n_head, y=None):
     """Backward of :func:`causal_attention_forward`; returns ``dqkv [B,T,3C]``.  ``P`` is whatever forward returned
     second: the fp32 LSE (flash path: one fused kernel + tiny prep/convert kernels; needs ``y``) or the bf16
     probabilities (materialised path: four batched GEMMs and one softmax-backward kernel)."""
+    if on_gpu(qkv) and qkv.dtype == torch.float32:
+        bf = torch.bfloat16
+        dqkv = causal_attention_backward(cast(grad_y.contiguous(), bf), cast(qkv, bf), P, n_head,
+                                         y=None if y is None else cast(y, bf))
+        return cast(dqkv, torch.float32)
     if P.dtype == torch.float32 and P.dim() == 3 and on_gpu(qkv):
         dqkv = ext().flash_bwd(grad_y.contiguous(), qkv, y, P, n_head)
         count_launch(3)

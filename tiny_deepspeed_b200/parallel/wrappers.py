@@ -140,7 +140,9 @@ class _ParallelWrapper(tnn.Module):
         if backend != "auto":
             return backend
         on_cuda = any(p.is_cuda for p in self.module.parameters())
-        if on_cuda and self.world_size > 1:
+        # the NVLink symmetric-memory kernels reduce bf16 (multimem.ld_reduce bf16x2); fp32 models go through NCCL
+        all_bf16 = all(p.dtype == torch.bfloat16 for p in self.module.parameters())
+        if on_cuda and self.world_size > 1 and all_bf16:
             try:
                 from . import symm
                 if symm.available():
