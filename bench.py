@@ -35,6 +35,8 @@ def parse():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--backend", default="auto", choices=["auto", "native", "dist"])
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"],
+                    help="parameter/compute dtype of BOTH arms; fp32 = the reference scripts' own dtype (ours: TF32 tcgen05 GEMMs)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--partition", default=None, choices=["greedy", "contiguous", "balanced"],
                     help="ownership planner (default: balanced for zero1/2, contiguous for zero3 so a layer is one fetch)")
@@ -87,6 +89,11 @@ MODEL_DIMS = {"tiny": (2, 2, 128), "small": (12, 12, 768), "medium": (24, 16, 10
 # ------------------------------------------------------------------------------------------------------
 # our arm
 # ------------------------------------------------------------------------------------------------------
+def _dt(args):
+    import torch
+    return torch.bfloat16 if args.dtype == "bf16" else torch.float32
+
+
 def build_ours(args, rank, world, device):
     import torch
     from collections import OrderedDict
@@ -97,11 +104,11 @@ def build_ours(args, rank, world, device):
     torch.manual_seed(1234)  # identical replicas; DDP also broadcasts from rank 0
     mode = args.mode
     if mode in ("single",):
-        model = GPT2Model(cfg).to(device=device, dtype=torch.bfloat16)
+        model = GPT2Model(cfg).to(device=device, dtype=_dt(args))
         opt = tds.AdamW(model.named_parameters(), lr=1e-5, weight_decay=1e-1)
         return cfg, model, opt
     if mode == "ddp":
-        model = GPT2Model(cfg).to(device=device, dtype=torch.bfloat16)
+        model = GPT2Model(cfg).to(device=device, dtype=_dt(args))
         model = tds.DDP(model, backend=args.backend)
         opt = tds.DDPAdamW(model.named_parameters(), lr=1e-5, weight_decay=1e-1)
         return cfg, model, opt
@@ -115,10 +122,10 @@ def build_ours(args, rank, world, device):
     O = {"zero1": tds.Zero1AdamW, "zero2": tds.Zero2AdamW, "zero3": tds.Zero3AdamW}[mode]
     if mode == "zero3":
         with torch.device("meta"):
-            model = GPT2Model(cfg).to(dtype=torch.bfloat16)
+            model = GPT2Model(cfg).to(dtype=_dt(args))
         model = W(model, parts, device=device, backend=args.backend)
     else:
-        model = GPT2Model(cfg).to(device=device, dtype=torch.bfloat16)
+        model = GPT2Model(cfg).to(device=device, dtype=_dt(args))
         model = W(model, parts, backend=args.backend)
     opt = O(model.module.named_parameters(), lr=1e-5, weight_decay=1e-1, param_part_table=parts, ranks_map=ranks_map)
     return cfg, model, opt
@@ -209,7 +216,7 @@ def run_ours(args):
         out = {
             "metric": "gpt2_train_tokens_per_sec", "value": tokens / (ms_step * 1e-3), "unit": "tokens/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
             "data": "synthetic random tokens, random-init weights", "impl": "ours",
             "config": {"model": f"gpt2-{args.model}", "global_batch": B * world, "seq_len": T,
                        "parallelism": f"{args.mode}{world}" if args.mode != "single" else "single",
@@ -262,7 +269,7 @@ def run_reference(args):
         y_host = torch.randint(0, cfg.vocab_size, (B, T)).pin_memory()
         x_dev, y_dev = x_host.to(device), y_host.to(device)
         mode = "ddp" if args.mode == "single" else args.mode
-        model = GPT2Model(cfg).to(device).to(torch.bfloat16)
+        model = GPT2Model(cfg).to(device).to(_dt(args))
         if mode == "ddp":
             model = core.DDP(model)
             opt = core.DDPAdamW(model.named_parameters(), lr=1e-5, weight_decay=1e-1)
@@ -309,10 +316,10 @@ def run_reference(args):
         if rank == 0:
             emit({"metric": "gpt2_train_tokens_per_sec", "value": tokens / (ms_step * 1e-3), "unit": "tokens/s",
                   "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+                  "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
                   "data": "synthetic random tokens, random-init weights", "impl": "reference",
                   "config": {"model": f"gpt2-{args.model}", "global_batch": B * world, "seq_len": T,
-                             "parallelism": f"{mode}{world}", "note": "unmodified reference, model.to(bfloat16)"},
+                             "parallelism": f"{mode}{world}", "note": f"unmodified reference, model.to({args.dtype})"},
                   "clocks": clk.summary(),
                   "e2e": {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
                           "h2d_bytes_per_step": int(x_host.numel() * 16), "d2h_bytes_per_step": 4},

@@ -81,14 +81,7 @@ def test_optimizer_in_backward_overlap_matches_plain_step():
         torch.testing.assert_close(a.float(), b.float(), rtol=1e-3, atol=1e-4, msg=n)
 
 
-def test_fp32_model_matches_oracle_and_trains():
-    """fp32 parameters (the reference's dtype, example/single_device/train.py:16): GEMMs run as TF32 on tcgen05, LN / CE /
-    Adam in fp32, the attention core on the bf16 flash kernels."""
-    torch.manual_seed(3)
-    cfg = gpt2_config("tiny", n_layer=2, n_head=4, n_embd=256, vocab_size=2048, block_size=256, bias=True)
-    m = GPT2Model(cfg).to(device="cuda", dtype=torch.float32)
-    x = torch.randint(0, cfg.vocab_size, (2, 256), device="cuda")
-    y = torch.randint(0, cfg.vocab_size, (2, 256), device="cuda")
+def _fp32_oracle_check(m, x, y):
     _, loss = m(x, y)
     loss.backward()
     got = {n: p.grad.clone() for n, p in m.named_parameters()}
@@ -106,9 +99,21 @@ def test_fp32_model_matches_oracle_and_trains():
         rel = (got[n] - p.grad).norm() / (p.grad.norm() + 1e-12)
         assert rel < 2e-2, (n, float(rel))
         p.grad = None
-    # drop the eager autograd graphs: their AccumulateGrad nodes are bound to the default stream and would otherwise be
-    # reused inside the capture (torch's usual "no default-stream autograd state before graph capture" rule)
-    del loss, rloss
+
+
+def test_fp32_model_matches_oracle_and_trains():
+    """fp32 parameters (the reference's dtype, example/single_device/train.py:16): GEMMs run as TF32 on tcgen05, LN / CE /
+    Adam in fp32, the attention core on the bf16 flash kernels."""
+    import gc
+    torch.manual_seed(3)
+    cfg = gpt2_config("tiny", n_layer=2, n_head=4, n_embd=256, vocab_size=2048, block_size=256, bias=True)
+    m = GPT2Model(cfg).to(device="cuda", dtype=torch.float32)
+    x = torch.randint(0, cfg.vocab_size, (2, 256), device="cuda")
+    y = torch.randint(0, cfg.vocab_size, (2, 256), device="cuda")
+    # in a helper so every eager autograd graph (logits, losses) is gone afterwards: their AccumulateGrad nodes are bound
+    # to the default stream and must not be reused inside the capture (torch's usual rule for CUDA-graph capture)
+    _fp32_oracle_check(m, x, y)
+    gc.collect()
     opt = tds.AdamW(m.named_parameters(), lr=1e-3, weight_decay=0.1)
     step = tds.TrainStep(m, opt, use_graph=True, warmup=2)
     losses = [float(step(x, y)) for _ in range(8)]

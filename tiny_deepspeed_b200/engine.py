@@ -100,8 +100,16 @@ class TrainStep:
     def _capture(self):
         torch.cuda.synchronize(self.device)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self._static_loss = self._eager(self._static_idx, self._static_tgt)
+        try:
+            with torch.cuda.graph(self.graph):
+                self._static_loss = self._eager(self._static_idx, self._static_tgt)
+        except RuntimeError as e:
+            self.graph = None
+            raise RuntimeError(
+                "TrainStep: CUDA-graph capture of the training step failed.  A frequent cause is an autograd graph built "
+                "on the default stream BEFORE the first TrainStep call that is still alive (e.g. a kept `logits`/`loss` "
+                "from a manual forward): its AccumulateGrad nodes are bound to that stream and cannot join the capture.  "
+                "Drop those tensors first, or construct TrainStep(..., use_graph=False).") from e
         # capture only records: the captured step has not executed yet
 
     def __call__(self, idx, targets):
