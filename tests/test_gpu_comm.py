@@ -231,3 +231,49 @@ def test_zero_native_under_cuda_graph(mode):
     res = run_gpu_distributed(_graph_zero, world=2, args=(mode,))
     losses, captured = res[0]
     assert captured and losses[-1] < losses[0] - 0.05, losses
+
+
+def _train_fp32(rank, world, mode):
+    """fp32 parameters (reference dtype): backend='auto' must pick the NCCL policy (the NVLink kernels reduce bf16) while
+    the math still runs on our TF32 GEMMs."""
+    import torch.distributed as dist
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    dev = torch.device("cuda", rank)
+    cfg = gpt2_config("tiny", n_layer=2, n_embd=256, n_head=4, vocab_size=2048, block_size=128)
+    with torch.device("meta"):
+        parts, _ = tds.partition_tensors(OrderedDict(GPT2Model(cfg).named_parameters()), num_parts=world)
+    torch.manual_seed(5)
+    model = GPT2Model(cfg).to(dev)                       # fp32
+    if mode == "ddp":
+        model = tds.DDP(model)
+        opt = tds.DDPAdamW(model.named_parameters(), lr=1e-3, weight_decay=0.1)
+    else:
+        model = tds.Zero2(model, parts)
+        opt = tds.Zero2AdamW(model.module.named_parameters(), lr=1e-3, weight_decay=0.1, param_part_table=parts,
+                             ranks_map=[f"cuda:{i}" for i in range(world)])
+    g = torch.Generator().manual_seed(100 + rank)
+    x = torch.randint(0, cfg.vocab_size, (2, 128), generator=g).to(dev)
+    y = torch.randint(0, cfg.vocab_size, (2, 128), generator=g).to(dev)
+    losses = []
+    for _ in range(5):
+        model.require_backward_grad_sync = True
+        _, loss = model(x, y)
+        loss.backward()
+        opt.step()
+        l = loss.detach().float().clone()
+        dist.all_reduce(l)
+        losses.append(float(l) / world)
+    final = {n: p.detach().float().cpu() for n, p in model.module.named_parameters()}
+    return losses, final, {"backend": model.backend, "dtype": str(next(model.parameters()).dtype)}
+
+
+@pytest.mark.parametrize("mode", ["ddp", "zero2"])
+def test_fp32_model_uses_nccl_policy_and_trains(mode):
+    world = _world()
+    out = run_gpu_distributed(_train_fp32, world=world, args=(mode,))
+    assert out[0][2] == {"backend": "dist", "dtype": "torch.float32"}
+    assert out[0][0][-1] < out[0][0][0]
+    for n, a in out[0][1].items():
+        for r in range(1, world):
+            torch.testing.assert_close(out[r][1][n], a, rtol=1e-5, atol=1e-6, msg=n)
