@@ -60,6 +60,27 @@ def _collectives(rank, world):
         if not torch.equal(flat[off:off + s], src):
             out["errors"].append(("broadcast", s, 0))
         off += (s + 63) // 64 * 64
+    # fp32 at a non-zero offset, odd size: all-reduce and reduce-to-owner (fp32 models)
+    nf, offf = 768 * 768 + 64, 4096
+    stb = symm.alloc((offf + nf) * 4, dev)
+    fb = stb.local.view(torch.float32)
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    xf = torch.randn(nf, device=dev, generator=g)
+    reff = xf.clone()
+    dist.all_reduce(reff)
+    fb[offf:offf + nf].copy_(xf)
+    comm.allreduce(stb, offf, nf, f32=True)
+    torch.cuda.synchronize()
+    if not torch.allclose(fb[offf:offf + nf], reff, rtol=1e-5, atol=1e-5):
+        out["errors"].append(("allreduce_f32_big", nf, float((fb[offf:offf + nf] - reff).abs().max())))
+    fb[offf:offf + nf].copy_(xf)
+    torch.cuda.synchronize(); dist.barrier()
+    comm.reduce_to(stb, offf, nf, 0, f32=True, scale=0.5)
+    torch.cuda.synchronize()
+    if rank == 0 and not torch.allclose(fb[offf:offf + nf], 0.5 * reff, rtol=1e-5, atol=1e-5):
+        out["errors"].append(("reduce_to_f32", nf, float((fb[offf:offf + nf] - 0.5 * reff).abs().max())))
+    if rank != 0 and not torch.equal(fb[offf:offf + nf], xf):
+        out["errors"].append(("reduce_to_f32 clobbered non-dst", nf, 0))
     # fp32 all-reduce
     stf = symm.alloc(4096 * 4, dev)
     f = stf.local.view(torch.float32)
@@ -79,7 +100,7 @@ def test_collective_kernels_match_nccl():
     print("multicast:", res[0]["multicast"])
 
 
-def _train(rank, world, mode, backend, steps):
+def _train(rank, world, mode, backend, steps, dtype=torch.bfloat16):
     import torch.distributed as dist
     import tiny_deepspeed_b200 as tds
     from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
@@ -90,7 +111,7 @@ def _train(rank, world, mode, backend, steps):
         meta = GPT2Model(cfg)
         parts, _ = tds.partition_tensors(OrderedDict(meta.named_parameters()), num_parts=world)
     with torch.device("meta"):
-        model = GPT2Model(cfg).to(torch.bfloat16)
+        model = GPT2Model(cfg).to(dtype)
     torch.cuda.reset_peak_memory_stats(dev)
     if mode == "zero3":
         model = tds.Zero3(model, parts, device=dev, init_seed=3, backend=backend)
@@ -133,11 +154,14 @@ def _train(rank, world, mode, backend, steps):
     return losses, final, checks
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float32], ids=["bf16", "fp32"])
 @pytest.mark.parametrize("mode", ["ddp", "zero1", "zero2", "zero3"])
-def test_native_matches_dist_backend(mode):
+def test_native_matches_dist_backend(mode, dtype):
+    """bf16: NVLS all-reduce / fused reduce->Adam->multicast.  fp32 (the reference's dtype): the .f32 NVLS kernels, reduce-to-
+    owner + multi-tensor Adam + owner multicast (ZeRO-1/2), push staging ring (ZeRO-3)."""
     world = _world()
-    nat = run_gpu_distributed(_train, world=world, args=(mode, "native", 5))
-    ref = run_gpu_distributed(_train, world=world, args=(mode, "dist", 5))
+    nat = run_gpu_distributed(_train, world=world, args=(mode, "native", 5, dtype))
+    ref = run_gpu_distributed(_train, world=world, args=(mode, "dist", 5, dtype))
     assert nat[0][2]["backend"] == "native" and ref[0][2]["backend"] == "dist"
     for r in range(world):
         assert all(v for k, v in nat[r][2].items() if k != "backend"), nat[r][2]
@@ -234,8 +258,7 @@ def test_zero_native_under_cuda_graph(mode):
 
 
 def _train_fp32(rank, world, mode):
-    """fp32 parameters (reference dtype): backend='auto' must pick the NCCL policy (the NVLink kernels reduce bf16) while
-    the math still runs on our TF32 GEMMs."""
+    """fp32 parameters (reference dtype) with backend='auto': the symmetric-memory policy in its fp32 form, TF32 GEMMs."""
     import torch.distributed as dist
     import tiny_deepspeed_b200 as tds
     from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
@@ -269,10 +292,10 @@ def _train_fp32(rank, world, mode):
 
 
 @pytest.mark.parametrize("mode", ["ddp", "zero2"])
-def test_fp32_model_uses_nccl_policy_and_trains(mode):
+def test_fp32_model_auto_backend_trains(mode):
     world = _world()
     out = run_gpu_distributed(_train_fp32, world=world, args=(mode,))
-    assert out[0][2] == {"backend": "dist", "dtype": "torch.float32"}
+    assert out[0][2] == {"backend": "native", "dtype": "torch.float32"}
     assert out[0][0][-1] < out[0][0][0]
     for n, a in out[0][1].items():
         for r in range(1, world):

@@ -133,10 +133,13 @@ __global__ void __launch_bounds__(kCommThreads) allreduce_kernel(const __grid_co
   constexpr int U = 8;
   const long long stride = (long long)gridDim.x * blockDim.x * U;
   for (long long base = v0 + (long long)blockIdx.x * blockDim.x * U + threadIdx.x; base < v1; base += stride) {
-    if (b.mc && !F32 && scale == 1.f) {
+    if (b.mc && scale == 1.f) {
       uint4 v[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) { const long long i = base + (long long)u * blockDim.x; if (i < v1) v[u] = mm_ld_reduce_bf16((const char*)b.mc + boff + i * 16); }
+      for (int u = 0; u < U; ++u) {
+        const long long i = base + (long long)u * blockDim.x;
+        if (i < v1) v[u] = F32 ? mm_ld_reduce_f32((const char*)b.mc + boff + i * 16) : mm_ld_reduce_bf16((const char*)b.mc + boff + i * 16);
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) { const long long i = base + (long long)u * blockDim.x; if (i < v1) mm_st((char*)b.mc + boff + i * 16, v[u]); }
     } else {

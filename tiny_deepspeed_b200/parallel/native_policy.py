@@ -64,8 +64,14 @@ class NativePolicy(CommPolicy):
         named = [(n, p) for n, p in model.named_parameters()]
         p0 = next(p for _, p in named if p.numel() > 0)
         self.device, self.dtype = p0.device, p0.dtype
-        if self.dtype != torch.bfloat16:
-            raise NotImplementedError("native backend trains bf16 parameters (fp32 master weights live in the optimizer)")
+        if self.dtype not in (torch.bfloat16, torch.float32):
+            raise NotImplementedError("native backend trains bf16 (fp32 master weights in the optimizer) or fp32 parameters")
+        if any(p.dtype != self.dtype for _, p in named):
+            raise NotImplementedError("native backend needs one parameter dtype for the flat symmetric buffers")
+        # fp32 models: the same NVLS kernels in their .f32 form (multimem.ld_reduce.add.v4.f32); the fused
+        # reduce->Adam->multicast kernel is bf16-parameter only, fp32 takes reduce-to-owner + the multi-tensor Adam
+        self.f32 = self.dtype == torch.float32
+        self.esize = 4 if self.f32 else 2
         self.table = table or {n: 0 for n, _ in named}
         self.comm = symm.Comm(self.device, group)
         self.comm_stream = torch.cuda.Stream(self.device)
@@ -91,10 +97,10 @@ class NativePolicy(CommPolicy):
         else:
             self.poff = dict(self.goff)
             self.ptotal = self.gtotal
-        self.G = symm.alloc(self.gtotal * 2, self.device, group)
-        self.P = symm.alloc(self.ptotal * 2, self.device, group)
-        self.gflat = self.G.local.view(torch.bfloat16)
-        self.pflat = self.P.local.view(torch.bfloat16)
+        self.G = symm.alloc(self.gtotal * self.esize, self.device, group)
+        self.P = symm.alloc(self.ptotal * self.esize, self.device, group)
+        self.gflat = self.G.local.view(self.dtype)
+        self.pflat = self.P.local.view(self.dtype)
 
         # ---- move parameters into the symmetric buffer (in place: the model keeps its Parameter objects) ----
         with torch.no_grad():
@@ -118,7 +124,7 @@ class NativePolicy(CommPolicy):
         cur, cur_bytes = [], 0
         for n in reversed(self.names):
             cur.append(n)
-            cur_bytes += _pad(self.numel[n]) * 2
+            cur_bytes += _pad(self.numel[n]) * self.esize
             if cur_bytes >= bucket_bytes:
                 self.buckets.append(cur)
                 cur, cur_bytes = [], 0
@@ -132,7 +138,7 @@ class NativePolicy(CommPolicy):
         self._seq, self._seq_frozen, self._pos, self._fetched = [], False, 0, {}
         self._groups, self._group_of = [], {}
         if mode == "zero3" and self.fetch == "push" and self.world > 1:
-            self.slot_bytes = (max(_pad(v) for v in self.numel.values()) * 2 + 4095) // 4096 * 4096
+            self.slot_bytes = (max(_pad(v) for v in self.numel.values()) * self.esize + 4095) // 4096 * 4096
             self.S = symm.alloc(self.nslots * self.slot_bytes, self.device, group)
         self._reset_round()
         self._accumulated = set()      # names holding un-synced micro-batch gradients
@@ -218,14 +224,15 @@ class NativePolicy(CommPolicy):
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
             if not self.comm_stub:
-                self.comm.allreduce(self.G, lo, hi - lo, scale=self.scale, blocks=blocks or self.comm_blocks, channel=0)
+                self.comm.allreduce(self.G, lo, hi - lo, f32=self.f32, scale=self.scale, blocks=blocks or self.comm_blocks,
+                                    channel=0)
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
         self._bucket_event[b] = ev
         self._launch_order.append(b)
         self._launched[b] = True
         self.stats["allreduce_launches"] += 1
-        self.stats["bytes"] += (hi - lo) * 2
+        self.stats["bytes"] += (hi - lo) * self.esize
 
     def flush_async(self):
         """DDP: queue the all-reduce of the last (still open) buckets WITHOUT joining the communication stream and
@@ -265,7 +272,7 @@ class NativePolicy(CommPolicy):
         elif self.mode != "ddp" and self._synced_any and self._opt_state is None:
             # generic (non-fused) optimizer: reduce every tensor onto its owner with our kernel, tensor by tensor
             for n in self.names:
-                self.comm.reduce_to(self.G, self.goff[n], _pad(self.numel[n]), self._owner(n), scale=self.scale,
+                self.comm.reduce_to(self.G, self.goff[n], _pad(self.numel[n]), self._owner(n), f32=self.f32, scale=self.scale,
                                     blocks=self.comm_blocks, channel=0)
             self._accumulated.clear()
             self._reset_round()
@@ -282,7 +289,7 @@ class NativePolicy(CommPolicy):
                 return param.data
             # alias of the OWNER's memory (NVLink peer mapping): the consuming GEMM's TMA producer pulls the weight
             # tile by tile straight into shared memory (all-gather fused into the GEMM; M/128 x NVLink re-reads)
-            t = self.P.peer(owner, self.shape[n], self.dtype, self.poff[n] * 2)
+            t = self.P.peer(owner, self.shape[n], self.dtype, self.poff[n] * self.esize)
             t._tds_remote = True
             return t
         # ---- owner-push mode: the owner multicasts a GROUP of consecutively used tensors (a contiguous byte range of
@@ -311,14 +318,14 @@ class NativePolicy(CommPolicy):
         if owner == self.rank:
             return param.data
         grp = self._groups[g]
-        off = (g % self.nslots) * self.slot_bytes + (self.poff[n] - grp["lo"]) * 2
-        return self.S.local[off: off + self.numel[n] * 2].view(self.dtype).view(self.shape[n])
+        off = (g % self.nslots) * self.slot_bytes + (self.poff[n] - grp["lo"]) * self.esize
+        return self.S.local[off: off + self.numel[n] * self.esize].view(self.dtype).view(self.shape[n])
 
     def _launch_fetch(self, g):
         grp = self._groups[g]
         owner, slot = grp["owner"], g % self.nslots
-        nbytes = (grp["hi"] - grp["lo"]) * 2
-        src = self.pflat.data_ptr() + grp["lo"] * 2 if owner == self.rank else 0
+        nbytes = (grp["hi"] - grp["lo"]) * self.esize
+        src = self.pflat.data_ptr() + grp["lo"] * self.esize if owner == self.rank else 0
         # everything enqueued so far on the compute stream precedes the push: the slot's previous readers and the
         # optimizer update of the source range are therefore complete when the owner starts writing
         self.comm_stream.wait_stream(torch.cuda.current_stream(self.device))
@@ -335,7 +342,8 @@ class NativePolicy(CommPolicy):
     def _build_groups(self):
         """Merge the recorded use sequence into fetch groups: consecutive uses owned by the same rank whose byte ranges
         (in the owner's region) stay within one staging slot and leave gaps of at most `gap` elements."""
-        gap, cap = 1 << 19, min(self.slot_bytes // 2, 8 << 20)      # elements: <= 16 MB per push keeps the pipeline fine-grained
+        # elements: <= 16 MB per push keeps the pipeline fine-grained
+        gap, cap = 1 << 19, min(self.slot_bytes // self.esize, (16 << 20) // self.esize)
         groups, group_of = [], {}
         for pos, n in enumerate(self._seq):
             lo, hi, owner = self.poff[n], self.poff[n] + _pad(self.numel[n]), self._owner(n)
@@ -364,10 +372,31 @@ class NativePolicy(CommPolicy):
     def release(self, param, full):
         return
 
+    # ------------------------------------------------------------------------------------------ generic optimizer path
+    def broadcast_params(self):
+        """ZeRO-1/2 without the fused step (SGD, amsgrad, fp32 parameters): every owner multicasts its freshly updated
+        tensors; consecutive tensors of one owner travel as one contiguous byte range (one kernel each).  Replaces the
+        reference's per-tensor blocking ``dist.broadcast`` (zero1/optim.py:20-34)."""
+        if self.mode not in ("zero1", "zero2") or self.world == 1:
+            return
+        if getattr(self, "_bcast_ranges", None) is None:
+            ranges = []
+            for n in self.names:
+                lo, hi, owner = self.poff[n], self.poff[n] + _pad(self.numel[n]), self._owner(n)
+                if ranges and ranges[-1][2] == owner and ranges[-1][1] == lo:
+                    ranges[-1][1] = hi
+                else:
+                    ranges.append([lo, hi, owner])
+            self._bcast_ranges = ranges
+        if self.comm_stub:
+            return
+        for lo, hi, owner in self._bcast_ranges:
+            self.comm.broadcast(self.P, lo * self.esize, (hi - lo) * self.esize, owner, blocks=self.comm_blocks, channel=0)
+
     # ------------------------------------------------------------------------------------------ fused optimizer step
     def owns_optimizer_state(self, opt) -> bool:
         from ..optim.adamw import AdamW
-        return self.mode != "ddp" and self.world > 1 and isinstance(opt, AdamW) and not opt.amsgrad
+        return self.mode != "ddp" and self.world > 1 and isinstance(opt, AdamW) and not opt.amsgrad and not self.f32
 
     def _ensure_opt_state(self, opt):
         if self._opt_state is not None:
@@ -396,7 +425,7 @@ class NativePolicy(CommPolicy):
         """ZeRO-1/2/3 + Adam: reduce -> Adam -> (multicast) in one kernel sequence.  Returns False when this
         policy/optimizer pair must take the generic path."""
         from ..optim.adamw import AdamW
-        if self.mode == "ddp" or self.world == 1 or not isinstance(opt, AdamW) or opt.amsgrad:
+        if self.mode == "ddp" or self.world == 1 or not isinstance(opt, AdamW) or opt.amsgrad or self.f32:
             return False
         if not self._synced_any:
             return False

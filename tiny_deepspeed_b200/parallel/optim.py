@@ -65,6 +65,10 @@ class _Sharded:
     def _post_update(self):
         if self._mode in ("ddp", "zero3") or self.world_size == 1:
             return
+        pol = self._native_policy()
+        if pol is not None:
+            pol.broadcast_params()        # our multicast kernel over the symmetric parameter buffer, owner by owner
+            return
         handles = []
         for name, p in self.parameters.items():
             src = self.param_part_table[name]

@@ -140,9 +140,10 @@ class _ParallelWrapper(tnn.Module):
         if backend != "auto":
             return backend
         on_cuda = any(p.is_cuda for p in self.module.parameters())
-        # the NVLink symmetric-memory kernels reduce bf16 (multimem.ld_reduce bf16x2); fp32 models go through NCCL
-        all_bf16 = all(p.dtype == torch.bfloat16 for p in self.module.parameters())
-        if on_cuda and self.world_size > 1 and all_bf16:
+        # the flat symmetric buffers need one dtype: bf16 (multimem.ld_reduce bf16x2) or fp32 (.v4.f32)
+        dts = {p.dtype for p in self.module.parameters()}
+        uniform = len(dts) == 1 and next(iter(dts)) in (torch.bfloat16, torch.float32)
+        if on_cuda and self.world_size > 1 and uniform:
             try:
                 from . import symm
                 if symm.available():
