@@ -344,3 +344,16 @@ def test_attention_fp32_model_dtype():
     g = ops.causal_attention_backward(dy, qkv.detach(), P, nh, y=y)
     assert g.dtype == torch.float32
     assert _rel(g, gr) < 2e-2
+
+
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3])
+def test_gemm_reduce_out_epilogue(cfg):
+    """Experimental fused reduce epilogue: the fp32 product is ADDED into the destination by the TMA (the same op targets a
+    peer's gradient shard in the multi-GPU reduce-scatter path); two launches accumulate, ragged edges are clipped."""
+    for (M, N, K) in [(768, 3072, 1024), (200, 136, 256)]:
+        dy, x = _rand(K, M), _rand(K, N)                       # dW = dY^T X : both operands MN-major
+        ref = dy.float().t() @ x.float()
+        out = torch.full((M, N), 0.5, device=_dev(), dtype=torch.float32)
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, reduce_out=True, config=cfg)
+        ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, reduce_out=True, config=cfg, alpha=0.5)
+        torch.testing.assert_close(out, 0.5 + 1.5 * ref, rtol=1e-3, atol=2e-2)

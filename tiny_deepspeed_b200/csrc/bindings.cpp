@@ -56,7 +56,7 @@ GemmOperand operand(const Tensor& t, bool mn, int64_t& rows_out, int64_t& k_out,
 
 void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, const c10::optional<Tensor>& bias,
           const c10::optional<Tensor>& aux, int64_t epi, bool accumulate, double alpha, int64_t config, int64_t tri,
-          int64_t cluster) {
+          int64_t cluster, bool reduce_out) {
   check_cuda(a, "a"); check_cuda(b, "b"); check_cuda(d, "d");
   c10::cuda::CUDAGuard guard(a.device());
   GemmParams p{};
@@ -91,6 +91,10 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, con
   p.epi = (int)epi; p.accumulate = accumulate; p.alpha = (float)alpha;
   p.M = (int)M; p.N = (int)N; p.K = (int)K; p.batch = (int)(a1 * a2); p.nbatch2 = (int)a2;
   p.config = (int)config; p.tri = (int)tri; p.cluster_m = (int)cluster;
+  p.reduce_out = reduce_out;
+  if (reduce_out)
+    TORCH_CHECK(d.scalar_type() == at::kFloat && d.dim() == 2 && a.scalar_type() == at::kBFloat16 && !p.bias && !p.aux,
+                "gemm(reduce_out): bf16 operands, fp32 2-D destination, no epilogue functor");
   gemm_bf16(p, cur_stream());
   check_launch("gemm");
 }

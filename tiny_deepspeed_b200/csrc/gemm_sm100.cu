@@ -87,7 +87,11 @@ __device__ __forceinline__ float ld1_any(const void* base, long long idx, int f3
 }
 
 // F32 = fp32 operands (kind::tf32): compile-time so the bf16 instantiation keeps its fully unrolled producer / issue loops
-template <int BN, bool F32>
+// RED = reduce-scatter epilogue (EXPERIMENTAL, opt-in, see ops.gemm(reduce_out=True)): the fp32 tile is added into the
+//       destination by the TMA (cp.reduce.async.bulk.tensor .add) instead of stored; the destination may be ANOTHER rank's
+//       copy of a symmetric gradient shard, so the dW GEMM of every rank accumulates straight into the owner over NVLink,
+//       tile by tile, while the GEMM is still running.  Compile-time so the default instantiations stay byte-identical.
+template <int BN, bool F32, bool RED>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
@@ -267,7 +271,33 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const bool row_ok = m < g.M;
       const long long d_off = (long long)b1 * g.dbs1 + (long long)b2 * g.dbs2 + (long long)m * g.ldd;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
-      if (g.tma_store) {
+      if constexpr (RED) {
+        // ---- reduce path: 32 x 32 fp32 slabs (128-byte rows, SWIZZLE_128B) -> TMA reduce-add into (peer) global memory ----
+#pragma unroll 1
+        for (int slab = 0; slab < BN / 32; ++slab) {
+          const int ns = n0 + slab * 32;
+          if (ns >= g.N) break;
+          const uint32_t dbuf = my_stage0 + sbuf_toggle * kStageBufBytes;
+          sbuf_toggle ^= 1u;
+          if (lane == 0) ptx::bulk_wait_read<1>();
+          __syncwarp();
+          uint32_t raw[32];
+          ptx::tmem_ld_32x32(t_row + slab * 32, raw);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16) {
+            const float4 v = make_float4(__uint_as_float(raw[c16 * 4]) * g.alpha, __uint_as_float(raw[c16 * 4 + 1]) * g.alpha,
+                                         __uint_as_float(raw[c16 * 4 + 2]) * g.alpha, __uint_as_float(raw[c16 * 4 + 3]) * g.alpha);
+            ptx::st_shared_16(dbuf + (uint32_t)lane * 128u + ((((uint32_t)c16) ^ (uint32_t)(lane & 7)) << 4), v);
+          }
+          ptx::fence_proxy_async();
+          __syncwarp();
+          if (lane == 0 && m0 + q * 32 < g.M) {     // rows / columns past M, N are clipped by the tensor map
+            ptx::tma_reduce_add_2d(&tma_d, dbuf, ns, m0 + q * 32);
+            ptx::bulk_commit();
+          }
+        }
+      } else if (g.tma_store) {
         // ---- coalesced path: registers -> 128B-swizzled smem slab (32 rows x 64 cols) -> TMA store ------------------
 #pragma unroll 1
         for (int slab = 0; slab < ((g.dbg & 4) ? 0 : BN / 64); ++slab) {
@@ -442,7 +472,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
     }
-    if (lane == 0) ptx::bulk_wait_read<0>();     // staging smem must outlive the last TMA store's reads
+    if (lane == 0) {
+      if constexpr (RED) {
+        // the adds must be PERFORMED (not just read out of smem) before this grid counts as complete: the consumer is a
+        // kernel on another GPU that synchronises through flags only
+        asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        __threadfence_system();
+      } else {
+        ptx::bulk_wait_read<0>();     // staging smem must outlive the last TMA store's reads
+      }
+    }
     __syncwarp();
   }
 
@@ -557,22 +596,22 @@ static int max_clusters(int cm) {
   at[0].val.clusterDim.x = cm; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
   cache[cm] = n;
   return n;
 }
 
-template <int BN, bool F32>
+template <int BN, bool F32, bool RED = false>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                    const GemmDev& g, int tiles, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_kernel<BN, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+    cudaFuncSetAttribute(gemm_kernel<BN, F32, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
     attr_done = true;
   }
   if (g.cm == 1) {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    launch_k(gemm_kernel<BN, F32>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
+    launch_k(gemm_kernel<BN, F32, RED>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
     return;
   }
   // cluster launch: cm consecutive CTAs = cm consecutive M tiles of one N tile; grid is a whole number of clusters
@@ -590,7 +629,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32>, ta, tb, td, tx, g);
+  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32, RED>, ta, tb, td, tx, g);
 }
 
 // cluster size along M: B-tile multicast divides L2->SM (or NVLink, for a ZeRO-3 peer weight) operand traffic by cm
@@ -599,7 +638,7 @@ static int pick_cluster(const GemmParams& p, int bn) {
   // measured on B200 (profiles/r1_gemm_cluster_sweep.md): at M = 1024 the GPT-2 GEMMs are latency-, not L2-bound, and
   // cluster launch costs more than the multicast saves -> off unless requested
   int want = p.cluster_m > 0 ? p.cluster_m : (env >= 0 ? env : 1);
-  if (want <= 1 || p.tri != 0 || p.batch != 1 || p.in_dtype == kF32) return 1;
+  if (want <= 1 || p.tri != 0 || p.batch != 1 || p.in_dtype == kF32 || p.reduce_out) return 1;
   const int m_tiles = (p.M + BM - 1) / BM;
   int cm = 8;
   while (cm > 1 && (cm > want || m_tiles % cm != 0 || (bn / cm) % 8 != 0)) cm >>= 1;
@@ -644,7 +683,14 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   static const int no_tma_store = getenv("TDS_GEMM_DIRECT_STORE") ? atoi(getenv("TDS_GEMM_DIRECT_STORE")) : 0;
   const bool aligned = (p.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(p.d) & 15) == 0) && (p.N % 8 == 0) &&
                        (p.d_batch_stride % 8 == 0) && (p.d_batch_stride2 % 8 == 0);
-  if (!no_tma_store && p.d_dtype == kBF16 && !p.accumulate && aligned && !g.io_f32) {
+  if (p.reduce_out) {
+    // fp32 [M, N] destination (possibly peer-mapped), 32 x 32 boxes; bf16 operands only, no batch, no epilogue functor
+    if (f32 || p.d_dtype != kF32 || p.batch != 1 || p.bias || p.aux || (p.ldd % 4) != 0 ||
+        (reinterpret_cast<uintptr_t>(p.d) & 15) != 0 || !make_map_f32_2d(&td, p.d, p.M, p.N, p.ldd, 32, 32)) {
+      fprintf(stderr, "[tds] gemm: reduce_out needs bf16 operands and a 16-byte aligned fp32 [M,N] destination\n");
+      abort();
+    }
+  } else if (!no_tma_store && p.d_dtype == kBF16 && !p.accumulate && aligned && !g.io_f32) {
     GemmOperand od{p.d, p.ldd, p.d_batch_stride, p.d_batch_stride2, false};
     bool ok = make_map(&td, od, p.M, p.N, nb1, nb2, 32);
     if (ok && g.epi != EPI_NONE) {
@@ -655,7 +701,12 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
     }
     g.tma_store = ok ? 1 : 0;
   }
-  if (f32) {
+  if (p.reduce_out) {
+    if (cfg == 0) launch<64, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    else if (cfg == 1) launch<128, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    else if (cfg == 2) launch<256, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    else launch<192, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
+  } else if (f32) {
     if (cfg == 0) launch<64, true>(ta, tb, td, tx, g, (int)tiles, stream);
     else if (cfg == 1) launch<128, true>(ta, tb, td, tx, g, (int)tiles, stream);
     else if (cfg == 2) launch<256, true>(ta, tb, td, tx, g, (int)tiles, stream);

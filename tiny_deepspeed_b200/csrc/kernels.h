@@ -25,6 +25,7 @@ struct GemmParams {
   void* aux;  int64_t ld_aux;   // [M,N] (no batch) or nullptr
   int epi;                // EPI_* (see ops/__init__.py)
   bool accumulate;        // D += result
+  bool reduce_out;        // EXPERIMENTAL: D (fp32, may be peer memory) += result via TMA reduce-add (fused reduce-scatter epilogue)
   float alpha;
   int M, N, K, batch, nbatch2;
   int config;             // tile configuration index, -1 = heuristic

@@ -59,16 +59,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
          out: Optional[torch.Tensor] = None, out_dtype: Optional[torch.dtype] = None,
          bias: Optional[torch.Tensor] = None, aux: Optional[torch.Tensor] = None,
          epi: int = EPI_NONE, accumulate: bool = False, alpha: float = 1.0,
-         config: Optional[int] = None, tri: int = 0, cluster: int = 0) -> torch.Tensor:
+         config: Optional[int] = None, tri: int = 0, cluster: int = 0, reduce_out: bool = False) -> torch.Tensor:
     """General (optionally batched) GEMM ``D[m,n] = alpha * sum_k A(m,k) * B(n,k)`` (+epilogue).
 
     ``a`` is stored ``[.., M, K]`` (K-major) or, with ``a_mn=True``, ``[.., K, M]`` (MN-major);
     likewise ``b`` is ``[.., N, K]`` or ``[.., K, N]``.  The inner stride must be 1, the other
     strides are free (so q/k/v head views of a packed qkv buffer are consumed in place).
     On CUDA this is one launch of the persistent tcgen05 kernel (csrc/gemm_sm100.cu).
+
+    ``reduce_out=True`` (experimental): ``out`` is an fp32 ``[M,N]`` tensor — possibly another rank's copy of a symmetric
+    buffer — and the product is *added* into it by the epilogue's TMA reduce (fused GEMM -> reduce-scatter).
     """
     if on_gpu(a, b):
+        if reduce_out or getattr(out, "_tds_reduce", False):
+            return _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, None, None, EPI_NONE, False, alpha, config, 0, 1, True)
         return _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alpha, config, tri, cluster)
+    if reduce_out:
+        accumulate = True
     A = a.transpose(-1, -2) if a_mn else a
     Bm = b.transpose(-1, -2) if b_mn else b
     acc = torch.matmul(A.float(), Bm.float().transpose(-1, -2)) * alpha
@@ -91,7 +98,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
-def _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alpha, config, tri=0, cluster=0):
+def _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alpha, config, tri=0, cluster=0, reduce_out=False):
     if getattr(b, "_tds_remote", False):
         # B aliases a peer GPU's memory (ZeRO-3 direct-fetch mode).  TMA *multicast* sourced from peer-mapped memory
         # wedged the GPU in testing (2xB200, r1), so the peer-fetch GEMM always runs with plain per-CTA TMA loads.
@@ -107,7 +114,7 @@ def _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alp
     if out is None:
         out = torch.empty(shape, device=a.device, dtype=out_dtype or a.dtype)
     ext().gemm(a, b, out, a_mn, b_mn, bias, aux, int(epi), bool(accumulate), float(alpha),
-               -1 if config is None else int(config), int(tri), int(cluster))
+               -1 if config is None else int(config), int(tri), int(cluster), bool(reduce_out))
     count_launch()
     return out
 
