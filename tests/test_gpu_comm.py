@@ -100,8 +100,10 @@ def test_collective_kernels_match_nccl():
     print("multicast:", res[0]["multicast"])
 
 
-def _train(rank, world, mode, backend, steps, dtype=torch.bfloat16):
+def _train(rank, world, mode, backend, steps, dtype=torch.bfloat16, env=None):
+    import os
     import torch.distributed as dist
+    os.environ.update(env or {})
     import tiny_deepspeed_b200 as tds
     from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
     from tiny_deepspeed_b200.parallel import materialize_
@@ -300,3 +302,22 @@ def test_fp32_model_auto_backend_trains(mode):
     for n, a in out[0][1].items():
         for r in range(1, world):
             torch.testing.assert_close(out[r][1][n], a, rtol=1e-5, atol=1e-6, msg=n)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TDS_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental fused GEMM -> reduce-scatter path: opt in with TDS_TEST_EXPERIMENTAL=1")
+@pytest.mark.parametrize("mode", ["zero1", "zero2", "zero3"])
+def test_fused_reduce_scatter_matches_dist_backend(mode):
+    """TDS_FUSED_RS=1: every rank's dW GEMM epilogue TMA-reduce-adds its fp32 tile into the owner's buffer over NVLink and the
+    fused step consumes the local sum.  Not run by default until it has been validated on multi-GPU hardware."""
+    world = _world()
+    nat = run_gpu_distributed(_train, world=world, args=(mode, "native", 5, torch.bfloat16, {"TDS_FUSED_RS": "1"}), timeout=180)
+    ref = run_gpu_distributed(_train, world=world, args=(mode, "dist", 5))
+    assert nat[0][2]["backend"] == "native"
+    assert nat[0][0] == pytest.approx(ref[0][0], rel=2e-2, abs=2e-2), (nat[0][0], ref[0][0])
+    for n in nat[0][1]:
+        a, b = nat[0][1][n], ref[0][1][n]
+        rel = (a - b).norm() / (b.norm() + 1e-9)
+        assert rel < 2e-2, (mode, n, float(rel))
+        for r in range(1, world):
+            assert torch.equal(nat[r][1][n], a), (mode, n, r)

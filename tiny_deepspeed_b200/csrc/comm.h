@@ -48,9 +48,17 @@ struct OwnedRanges {
   int blk_start[kMaxRanges + 1];
   int count;
 };
+struct OwnedRangesRS {            // fused reduce-scatter path only (separate type: the default kernel's parameter layout is untouched)
+  OwnedRanges r;
+  uint8_t rs[kMaxRanges];         // 1 = gradient already summed in the local fp32 buffer
+};
 void zero_fused_adam(const CommCtx& c, const SymmBuf& grads, const SymmBuf& params, const OwnedRanges& r, float* master,
                      float* exp_avg, float* exp_avg_sq, const AdamHyper& h, bool bcast_params, int channel,
                      cudaStream_t s);
+// EXPERIMENTAL variant for the GEMM -> reduce-scatter epilogue path (see comm_sm100.cu)
+void zero_fused_adam_rs(const CommCtx& c, const SymmBuf& grads, const SymmBuf& params, const SymmBuf& rs, const OwnedRangesRS& r,
+                        float* master, float* exp_avg, float* exp_avg_sq, const AdamHyper& h, bool bcast_params, int channel,
+                        cudaStream_t s);
 constexpr int kZeroChunk = 256 * 8 * 4;   // elements per CTA-iteration in zero_fused_adam
 
 }  // namespace tds

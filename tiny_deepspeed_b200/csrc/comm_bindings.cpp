@@ -99,6 +99,40 @@ int64_t py_zero_fused_adam(const PyComm& c, const PyBuf& grads, const PyBuf& par
   return launches;
 }
 
+// EXPERIMENTAL: ranges are [grad_off, numel, state_off, param_off, from_rs]
+int64_t py_zero_fused_adam_rs(const PyComm& c, const PyBuf& grads, const PyBuf& params, const PyBuf& rs,
+                              const std::vector<std::vector<int64_t>>& ranges, Tensor master, Tensor exp_avg,
+                              Tensor exp_avg_sq, double lr, double b1, double b2, double eps, double wd, const Tensor& step,
+                              bool decoupled, bool maximize, double grad_scale, bool bcast, int64_t channel) {
+  AdamHyper h{(float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (float)grad_scale, decoupled ? 1 : 0,
+              maximize ? 1 : 0, step.data_ptr<int>()};
+  float* mp = master.numel() ? master.data_ptr<float>() : nullptr;
+  float* m1 = exp_avg.numel() ? exp_avg.data_ptr<float>() : nullptr;
+  float* m2 = exp_avg_sq.numel() ? exp_avg_sq.data_ptr<float>() : nullptr;
+  int64_t launches = 0;
+  size_t i = 0;
+  do {
+    OwnedRangesRS RR{};
+    OwnedRanges& R = RR.r;
+    int cnt = 0, blk = 0;
+    while (i < ranges.size() && cnt < kMaxRanges) {
+      const auto& r = ranges[i];
+      TORCH_CHECK(r.size() == 5 && r[0] % 8 == 0 && r[1] % 8 == 0 && r[2] % 8 == 0 && r[3] % 8 == 0, "ranges must be 8-element aligned");
+      R.elem_off[cnt] = r[0]; R.numel[cnt] = r[1]; R.state_off[cnt] = r[2]; R.pelem_off[cnt] = r[3]; RR.rs[cnt] = r[4] ? 1 : 0;
+      R.blk_start[cnt] = blk;
+      blk += (int)((r[1] + kZeroChunk - 1) / kZeroChunk);
+      ++cnt; ++i;
+    }
+    R.blk_start[cnt] = blk;
+    R.count = cnt > 0 ? cnt : 1;
+    if (cnt == 0) { R.blk_start[0] = 0; R.blk_start[1] = 0; }
+    zero_fused_adam_rs(c.ctx, grads.buf, params.buf, rs.buf, RR, mp, m1, m2, h, bcast, (int)channel, cur_stream());
+    ++launches;
+  } while (i < ranges.size());
+  check_launch("zero_fused_adam_rs");
+  return launches;
+}
+
 }  // namespace
 
 void bind_comm(pybind11::module_& m) {
@@ -115,6 +149,7 @@ void bind_comm(pybind11::module_& m) {
   m.def("comm_barrier", &py_barrier);
   m.def("comm_push", &py_push);
   m.def("comm_zero_fused_adam", &py_zero_fused_adam);
+  m.def("comm_zero_fused_adam_rs", &py_zero_fused_adam_rs);
   m.attr("COMM_MAX_BLOCKS") = kCommMaxBlocks;
   m.attr("COMM_MAX_RANKS") = kMaxRanks;
 }

@@ -363,4 +363,100 @@ void zero_fused_adam(const CommCtx& c, const SymmBuf& grads, const SymmBuf& para
                                                         bcast_params ? 1 : 0, channel, work);
 }
 
+
+// =====================================================================================================
+// EXPERIMENTAL (opt-in TDS_FUSED_RS=1, not yet run on multi-GPU hardware): fused step for the GEMM -> reduce-scatter path.
+// Ranges flagged in R.rs were already summed over all ranks INTO this rank's fp32 reduction buffer `rs` (every rank's dW GEMM
+// epilogue TMA-reduce-adds its tile into the owner, gemm_sm100.cu RED variant), at the same offset as the optimizer state;
+// they are consumed from local memory and zeroed for the next step.  Unflagged ranges (embeddings, LayerNorm, biases) keep
+// the switch-reduced multimem path.  Kept as a separate kernel so the default one above stays byte-identical.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) zero_fused_adam_rs_kernel(const __grid_constant__ CommCtx c,
+                                                                 const __grid_constant__ SymmBuf grads,
+                                                                 const __grid_constant__ SymmBuf params,
+                                                                 const __grid_constant__ SymmBuf rs,
+                                                                 const __grid_constant__ OwnedRangesRS RR,
+                                                                 float* __restrict__ master, float* __restrict__ exp_avg,
+                                                                 float* __restrict__ exp_avg_sq,
+                                                                 const __grid_constant__ AdamHyper h, int bcast, int channel,
+                                                                 int work_blocks) {
+  const OwnedRanges& R = RR.r;
+  block_barrier(c, channel);                       // all ranks' backward kernels (and their remote reduce-adds) are complete
+  __shared__ float s_bc[2];
+  if (threadIdx.x == 0) {
+    const int step = *h.step_ptr;
+    s_bc[0] = 1.f - powf(h.beta1, (float)step);
+    s_bc[1] = rsqrtf(1.f - powf(h.beta2, (float)step));
+  }
+  __syncthreads();
+  const float bc1 = s_bc[0], bc2r = s_bc[1];
+  char* local_param = (char*)params.peer[c.rank];
+  float* local_rs = (float*)rs.peer[c.rank];
+  for (int wb = blockIdx.x; wb < work_blocks; wb += gridDim.x) {
+    const int t = find_range(R.blk_start, R.count, wb);
+    const long long base = (long long)(wb - R.blk_start[t]) * kZeroChunk;
+    const long long n = R.numel[t];
+    const long long end = base + kZeroChunk < n ? base + kZeroChunk : n;
+    const bool from_rs = RR.rs[t] != 0;
+    for (long long i = base + threadIdx.x * 8; i < end; i += 256 * 8) {
+      float g[8];
+      const long long so = R.state_off[t] + i;
+      if (from_rs) {
+        // written by remote atomics at this GPU's L2: read around L1, then clear for the next step
+        const float4 a = __ldcg(reinterpret_cast<const float4*>(local_rs + so));
+        const float4 b = __ldcg(reinterpret_cast<const float4*>(local_rs + so + 4));
+        g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+        __stcg(reinterpret_cast<float4*>(local_rs + so), make_float4(0.f, 0.f, 0.f, 0.f));
+        __stcg(reinterpret_cast<float4*>(local_rs + so + 4), make_float4(0.f, 0.f, 0.f, 0.f));
+      } else if (grads.mc) {
+        const uint4 raw = mm_ld_reduce_bf16((const char*)grads.mc + (size_t)(R.elem_off[t] + i) * 2);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] = 0.f;
+        acc_bf16x8(g, raw);
+      } else {
+        reduce_vec<false>(c, grads, (size_t)(R.elem_off[t] + i) * 2, g);
+      }
+      float w[8], m[8], v[8];
+      *reinterpret_cast<float4*>(w) = *reinterpret_cast<const float4*>(master + so);
+      *reinterpret_cast<float4*>(w + 4) = *reinterpret_cast<const float4*>(master + so + 4);
+      *reinterpret_cast<float4*>(m) = *reinterpret_cast<const float4*>(exp_avg + so);
+      *reinterpret_cast<float4*>(m + 4) = *reinterpret_cast<const float4*>(exp_avg + so + 4);
+      *reinterpret_cast<float4*>(v) = *reinterpret_cast<const float4*>(exp_avg_sq + so);
+      *reinterpret_cast<float4*>(v + 4) = *reinterpret_cast<const float4*>(exp_avg_sq + so + 4);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float gg = g[j] * h.grad_scale;
+        if (h.maximize) gg = -gg;
+        if (h.weight_decay != 0.f) {
+          if (h.decoupled) w[j] *= (1.f - h.lr * h.weight_decay);
+          else gg += h.weight_decay * w[j];
+        }
+        m[j] = h.beta1 * m[j] + (1.f - h.beta1) * gg;
+        v[j] = h.beta2 * v[j] + (1.f - h.beta2) * gg * gg;
+        w[j] -= (h.lr / bc1) * (m[j] / (sqrtf(v[j]) * bc2r + h.eps));
+      }
+      *reinterpret_cast<float4*>(master + so) = *reinterpret_cast<float4*>(w);
+      *reinterpret_cast<float4*>(master + so + 4) = *reinterpret_cast<float4*>(w + 4);
+      *reinterpret_cast<float4*>(exp_avg + so) = *reinterpret_cast<float4*>(m);
+      *reinterpret_cast<float4*>(exp_avg + so + 4) = *reinterpret_cast<float4*>(m + 4);
+      *reinterpret_cast<float4*>(exp_avg_sq + so) = *reinterpret_cast<float4*>(v);
+      *reinterpret_cast<float4*>(exp_avg_sq + so + 4) = *reinterpret_cast<float4*>(v + 4);
+      const uint4 o = pack_bf16x8(w);
+      const size_t poff = (size_t)(R.pelem_off[t] + i) * 2;
+      if (bcast) bcast_vec(c, params, poff, o);
+      else *reinterpret_cast<uint4*>(local_param + poff) = o;
+    }
+  }
+  __threadfence_system();
+  block_barrier(c, channel);                       // new parameters visible everywhere; every rank's reduction buffer is clear
+}
+
+void zero_fused_adam_rs(const CommCtx& c, const SymmBuf& grads, const SymmBuf& params, const SymmBuf& rs, const OwnedRangesRS& r,
+                        float* master, float* exp_avg, float* exp_avg_sq, const AdamHyper& h, bool bcast_params, int channel,
+                        cudaStream_t s) {
+  const int work = r.r.blk_start[r.r.count];
+  zero_fused_adam_rs_kernel<<<kCommMaxBlocks, 256, 0, s>>>(c, grads, params, rs, r, master, exp_avg, exp_avg_sq, h,
+                                                           bcast_params ? 1 : 0, channel, work);
+}
+
 }  // namespace tds

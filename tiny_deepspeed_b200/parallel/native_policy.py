@@ -45,6 +45,8 @@ def _pad(n: int) -> int:
 
 class NativePolicy(CommPolicy):
     is_native = True
+    fused_rs = False          # EXPERIMENTAL GEMM -> reduce-scatter fusion (TDS_FUSED_RS=1), see __init__
+    rs_names = frozenset()
 
     def __init__(self, mode: str, model: torch.nn.Module, *, table: Optional[Dict[str, int]] = None, group=None,
                  average: bool = False, bucket_bytes: int = 64 << 20, comm_blocks: int = 32):
@@ -140,6 +142,34 @@ class NativePolicy(CommPolicy):
         if mode == "zero3" and self.fetch == "push" and self.world > 1:
             self.slot_bytes = (max(_pad(v) for v in self.numel.values()) * self.esize + 4095) // 4096 * 4096
             self.S = symm.alloc(self.nslots * self.slot_bytes, self.device, group)
+        # ---- EXPERIMENTAL (TDS_FUSED_RS=1, not yet exercised on multi-GPU hardware): GEMM -> reduce-scatter fusion ------
+        # Every rank's dW GEMM epilogue adds its fp32 tile straight into the OWNER's reduction buffer over NVLink (TMA
+        # reduce-add into peer memory, gemm_sm100.cu RED variant), so the gradient reduction of the Linear weights overlaps
+        # backward tile by tile and the fused step reads an already-summed local buffer.  The buffer mirrors the layout of
+        # the owner's optimizer state.  Embedding / LayerNorm / bias gradients keep the multimem path.
+        self.fused_rs = (os.environ.get("TDS_FUSED_RS", "0") == "1" and mode != "ddp" and self.world > 1 and not self.f32)
+        if self.fused_rs:
+            from ..nn.modules import Linear
+            lin = {id(m.weight) for m in model.modules() if isinstance(m, Linear)}
+            self.rs_names = {n for n, p in named if id(p) in lin}
+            self.rs_off, tot = {}, [0] * self.world
+            for n in self.names:
+                o = self.table[n]
+                self.rs_off[n] = tot[o]
+                tot[o] += _pad(self.numel[n])
+            self.R = symm.alloc(max(max(tot), ALIGN) * 4, self.device, group)
+            self.R.local.zero_()
+            torch.cuda.synchronize(self.device)
+            self.comm.barrier()
+            rl = self.R.local.view(torch.float32)
+            self._rs_local, self._rs_view = {}, {}
+            for n in self.rs_names:
+                o, off = self.table[n], self.rs_off[n]
+                loc = rl[off: off + self.numel[n]].view(self.shape[n])
+                view = loc if o == self.rank else self.R.peer(o, self.shape[n], torch.float32, off * 4)
+                loc._tds_reduce = True
+                view._tds_reduce = True
+                self._rs_local[n], self._rs_view[n] = loc, view
         self._reset_round()
         self._accumulated = set()      # names holding un-synced micro-batch gradients
         self._opt_state = None
@@ -158,6 +188,8 @@ class NativePolicy(CommPolicy):
         n = self.G.local.numel() + self.P.local.numel() + self.comm.flags.local.numel()
         if hasattr(self, "S"):
             n += self.S.local.numel()
+        if getattr(self, "fused_rs", False):
+            n += self.R.local.numel()
         return int(n)
 
     # ------------------------------------------------------------------------------------------ helpers
@@ -176,10 +208,18 @@ class NativePolicy(CommPolicy):
     # ------------------------------------------------------------------------------------------ gradients
     def grad_out(self, param):
         n = self._name_of[id(param)]
+        if self.fused_rs and n in self.rs_names:
+            # the dW GEMM adds into the owner's fp32 buffer (ops.gemm sees `_tds_reduce`); stubbed runs stay rank-local
+            return (self._rs_local[n] if self.comm_stub else self._rs_view[n]), False
         return self.gview[n], (n in self._accumulated)
 
     def grad_ready(self, param, grad):
         n = self._name_of[id(param)]
+        if self.fused_rs and n in self.rs_names:               # already on its way to the owner
+            if getattr(param, "bwd_sync", False):
+                param.bwd_sync = False
+                self._synced_any = True
+            return
         if grad.data_ptr() != self.gview[n].data_ptr():        # op ignored `out` (should not happen): copy in
             if n in self._accumulated:
                 self.gview[n].add_(grad)
@@ -433,6 +473,26 @@ class NativePolicy(CommPolicy):
         opt.step_count += 1
         step_dev = opt._device_step(self.device)
         ctx, gbuf, pbuf = (self._solo_ctx, self._solo_g, self._solo_p) if self.comm_stub else (self.comm.ctx, self.G.buf, self.P.buf)
+        if self.fused_rs:
+            if "ranges_rs" not in st:
+                owned_rs = {n: int(n in self.rs_names) for n in st["owned"]}
+                st["ranges_rs"] = [r + [owned_rs[n]] for r, n in zip(st["ranges"], st["owned"])]
+            if self.comm_stub and not hasattr(self, "_solo_r"):
+                self._solo_r = ops.ext().SymmBuf([int(self.R.peer_ptrs[self.rank])], 0)
+            rbuf = self._solo_r if self.comm_stub else self.R.buf
+            launches = ops.ext().comm_zero_fused_adam_rs(
+                ctx, gbuf, pbuf, rbuf, st["ranges_rs"], st["master"], st["m"], st["v"],
+                float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
+                bool(opt.decoupled), bool(opt.maximize), float(opt.grad_scale * self.scale),
+                self.mode != "zero3", 1)
+            ops.count_launch(int(launches))
+            self.stats["fused_steps"] += 1
+            for p in self.params.values():
+                p.grad = None
+            self._accumulated.clear()
+            self._reset_round()
+            self._end_round_zero3()
+            return True
         launches = ops.ext().comm_zero_fused_adam(
             ctx, gbuf, pbuf, st["ranges"], st["master"], st["m"], st["v"],
             float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
