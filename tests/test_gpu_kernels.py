@@ -357,3 +357,18 @@ def test_gemm_reduce_out_epilogue(cfg):
         ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, reduce_out=True, config=cfg)
         ops.gemm(dy, x, a_mn=True, b_mn=True, out=out, reduce_out=True, config=cfg, alpha=0.5)
         torch.testing.assert_close(out, 0.5 + 1.5 * ref, rtol=1e-3, atol=2e-2)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("TDS_TEST_EXPERIMENTAL") != "1",
+                    reason="experimental CTA-pair (cta_group::2) GEMM: opt in with TDS_TEST_EXPERIMENTAL=1")
+def test_gemm_cta_pair_kernel_subprocess():
+    """csrc/gemm2_sm100.cu is compiled but has not run on hardware yet; checked in a child process (the switch is read once per
+    process) under a timeout so that a protocol bug cannot hang the suite."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, TDS_GEMM_2CTA="1")
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "gemm2_check.py"), "--no-baseline"], env=env,
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -1,4 +1,5 @@
 // torch <-> kernel glue for tiny_deepspeed_b200._C.  The only translation unit that sees torch headers.
+#include <cstdlib>
 #include <torch/extension.h>
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
@@ -95,6 +96,11 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, con
   if (reduce_out)
     TORCH_CHECK(d.scalar_type() == at::kFloat && d.dim() == 2 && a.scalar_type() == at::kBFloat16 && !p.bias && !p.aux,
                 "gemm(reduce_out): bf16 operands, fp32 2-D destination, no epilogue functor");
+  static const int use_pair = getenv("TDS_GEMM_2CTA") ? atoi(getenv("TDS_GEMM_2CTA")) : 0;   // experimental, default off
+  if (use_pair && gemm2_bf16(p, cur_stream())) {
+    check_launch("gemm2");
+    return;
+  }
   gemm_bf16(p, cur_stream());
   check_launch("gemm");
 }

@@ -34,6 +34,9 @@ struct GemmParams {
                           // 2 K-range ends at the tile's last row (P.V, dS.K), 3 K-range starts at the tile's first row (P^T.dY, dS^T.Q)
 };
 void gemm_bf16(const GemmParams& p, cudaStream_t stream);
+// EXPERIMENTAL CTA-pair (cta_group::2) variant, gemm2_sm100.cu: returns false without launching when the problem is outside
+// its coverage (then call gemm_bf16).  Opt-in through TDS_GEMM_2CTA=1 in the binding.
+bool gemm2_bf16(const GemmParams& p, cudaStream_t stream);
 int gemm_num_configs();
 
 // ---- elementwise / reductions (elementwise.cu) ----------------------------------------------------
