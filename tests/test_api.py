@@ -1,6 +1,4 @@
 """Public surface parity with the reference."""
-from collections import OrderedDict
-
 import torch
 
 EXPORTS = ["SGD", "AdamW", "DDPSGD", "DDPAdamW", "DDP", "Zero1SGD", "Zero1AdamW", "Zero1", "Zero2SGD",

@@ -1,6 +1,5 @@
 """Control flow, ownership, flag semantics and numerics of the four parallel modes on a gloo CPU process group
 (the "fake backend" of SURVEY §4 item 4).  World size 2 and 3."""
-import os
 from collections import OrderedDict
 
 import pytest

@@ -1,5 +1,4 @@
 """GPT-2 built from our layers vs an independent plain-PyTorch GPT-2 (same weights): loss + all gradients."""
-import math
 
 import torch
 import torch.nn as nn

@@ -1,6 +1,5 @@
 """CPU implementations of the op layer against autograd / F.* references (they are the oracle the GPU kernels are
 tested against, so they are tested themselves first)."""
-import math
 
 import pytest
 import torch

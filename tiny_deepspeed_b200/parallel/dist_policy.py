@@ -11,7 +11,7 @@ ARE reduced to the owner).  The B200 product path is ``native_poli
 from __future__ import annotations
 
 from collections import deque
-from typing import Dict, Optional
+from typing import Dict
 
 import torch
 import torch.distributed as dist

@@ -1,4 +1,4 @@
-import os, sys, math
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.nn.functional as F
 from tiny_deepspeed_b200 import ops

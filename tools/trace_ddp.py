@@ -1,6 +1,6 @@
 """Timeline check of compute/communication overlap (no nsys in the image: uses torch.profiler / CUPTI).
 torchrun --nproc-per-node N tools/trace_ddp.py [--mode ddp] ; rank 0 prints per-kernel timing of the comm kernels vs the rest."""
-import os, sys, json, argparse
+import os, sys, argparse
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
 import bench
