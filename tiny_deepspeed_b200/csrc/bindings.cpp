@@ -55,6 +55,13 @@ GemmOperand operand(const Tensor& t, bool mn, int64_t& rows_out, int64_t& k_out,
   return op;
 }
 
+static int g_use_pair = -1;   // CTA-pair (cta_group::2) kernel: -1 = read TDS_GEMM_2CTA on first use
+void set_gemm_pair(int64_t on) { g_use_pair = (int)on; }
+void gemm_set_prof_t(const c10::optional<Tensor>& buf) {
+  if (buf) TORCH_CHECK(buf->is_cuda() && buf->scalar_type() == at::kLong && buf->is_contiguous(), "prof buffer: int64 CUDA tensor");
+  gemm_set_prof(buf ? reinterpret_cast<long long*>(buf->data_ptr()) : nullptr);
+}
+
 void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, const c10::optional<Tensor>& bias,
           const c10::optional<Tensor>& aux, int64_t epi, bool accumulate, double alpha, int64_t config, int64_t tri,
           int64_t cluster, bool reduce_out) {
@@ -96,8 +103,8 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, con
   if (reduce_out)
     TORCH_CHECK(d.scalar_type() == at::kFloat && d.dim() == 2 && a.scalar_type() == at::kBFloat16 && !p.bias && !p.aux,
                 "gemm(reduce_out): bf16 operands, fp32 2-D destination, no epilogue functor");
-  static const int use_pair = getenv("TDS_GEMM_2CTA") ? atoi(getenv("TDS_GEMM_2CTA")) : 0;   // experimental, default off
-  if (use_pair && gemm2_bf16(p, cur_stream())) {
+  if (g_use_pair < 0) g_use_pair = getenv("TDS_GEMM_2CTA") ? atoi(getenv("TDS_GEMM_2CTA")) : 0;
+  if (g_use_pair && gemm2_bf16(p, cur_stream())) {
     check_launch("gemm2");
     return;
   }
@@ -363,6 +370,8 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "tiny_deepspeed_b200 sm_100a kernels";
   m.def("gemm", &gemm, "persistent tcgen05 GEMM");
   m.def("gemm_num_configs", &gemm_num_configs);
+  m.def("set_gemm_pair", &set_gemm_pair, "route eligible GEMMs through the cta_group::2 kernel (0/1)");
+  m.def("gemm_set_prof", &gemm_set_prof_t, "install / clear the per-CTA phase timestamp buffer (tools/gemm_timeline.py)");
   m.def("layernorm_fwd", &layernorm_fwd_);
   m.def("layernorm_bwd", &layernorm_bwd_);
   m.def("embedding_fwd", &embedding_fwd_);

@@ -20,6 +20,7 @@ struct CommCtx {
   uint32_t* flags[kMaxRanks];  // per-rank flag pads (symmetric, zero-initialised), >= kCommMaxBlocks*kMaxRanks*4 words
   int rank, world;
   int* error_flag;             // local sticky error word (timeouts)
+  long long spin_limit;        // SM cycles a flag wait may spin before it reports + traps (TDS_COMM_TIMEOUT_S, default 600 s)
 };
 
 // in-place sum all-reduce of buf[off, off+numel) (bf16, or fp32 when is_f32) across ranks; two-shot, one kernel

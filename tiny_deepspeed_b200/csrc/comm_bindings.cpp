@@ -3,6 +3,7 @@
 #include <ATen/cuda/CUDAContext.h>
 #include <c10/cuda/CUDAGuard.h>
 
+#include <stdlib.h>
 #include <vector>
 
 #include "comm.h"
@@ -28,6 +29,9 @@ struct PyComm {
     for (int r = 0; r < world; ++r) ctx.flags[r] = reinterpret_cast<uint32_t*>(flag_ptrs[r]);
     ctx.rank = (int)rank; ctx.world = (int)world;
     ctx.error_flag = err.data_ptr<int>();
+    const char* t = getenv("TDS_COMM_TIMEOUT_S");
+    const double secs = t ? atof(t) : 600.0;
+    ctx.spin_limit = (long long)((secs > 0.01 ? secs : 0.01) * 2.0e9);   // ~2 GHz SM clock
   }
 };
 struct PyBuf {
@@ -70,7 +74,8 @@ void py_barrier(const PyComm& c, int64_t channel) {
 int64_t py_zero_fused_adam(const PyComm& c, const PyBuf& grads, const PyBuf& params,
                            const std::vector<std::vector<int64_t>>& ranges, Tensor master, Tensor exp_avg,
                            Tensor exp_avg_sq, double lr, double b1, double b2, double eps, double wd, const Tensor& step,
-                           bool decoupled, bool maximize, double grad_scale, bool bcast, int64_t channel) {
+                           bool decoupled, bool maximize, double grad_scale, bool bcast, int64_t channel,
+                           int64_t min_launches) {
   AdamHyper h{(float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (float)grad_scale, decoupled ? 1 : 0,
               maximize ? 1 : 0, step.data_ptr<int>()};
   float* mp = master.numel() ? master.data_ptr<float>() : nullptr;
@@ -94,7 +99,8 @@ int64_t py_zero_fused_adam(const PyComm& c, const PyBuf& grads, const PyBuf& par
     if (cnt == 0) { R.blk_start[0] = 0; R.blk_start[1] = 0; }
     zero_fused_adam(c.ctx, grads.buf, params.buf, R, mp, m1, m2, h, bcast, (int)channel, cur_stream());
     ++launches;
-  } while (i < ranges.size());
+    // every rank must launch the SAME number of (barrier-carrying) kernels: pad up to the count of the rank owning most
+  } while (i < ranges.size() || launches < min_launches);
   check_launch("zero_fused_adam");
   return launches;
 }
@@ -103,7 +109,8 @@ int64_t py_zero_fused_adam(const PyComm& c, const PyBuf& grads, const PyBuf& par
 int64_t py_zero_fused_adam_rs(const PyComm& c, const PyBuf& grads, const PyBuf& params, const PyBuf& rs,
                               const std::vector<std::vector<int64_t>>& ranges, Tensor master, Tensor exp_avg,
                               Tensor exp_avg_sq, double lr, double b1, double b2, double eps, double wd, const Tensor& step,
-                              bool decoupled, bool maximize, double grad_scale, bool bcast, int64_t channel) {
+                              bool decoupled, bool maximize, double grad_scale, bool bcast, int64_t channel,
+                              int64_t min_launches) {
   AdamHyper h{(float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (float)grad_scale, decoupled ? 1 : 0,
               maximize ? 1 : 0, step.data_ptr<int>()};
   float* mp = master.numel() ? master.data_ptr<float>() : nullptr;
@@ -128,7 +135,7 @@ int64_t py_zero_fused_adam_rs(const PyComm& c, const PyBuf& grads, const PyBuf& 
     if (cnt == 0) { R.blk_start[0] = 0; R.blk_start[1] = 0; }
     zero_fused_adam_rs(c.ctx, grads.buf, params.buf, rs.buf, RR, mp, m1, m2, h, bcast, (int)channel, cur_stream());
     ++launches;
-  } while (i < ranges.size());
+  } while (i < ranges.size() || launches < min_launches);
   check_launch("zero_fused_adam_rs");
   return launches;
 }
@@ -152,4 +159,5 @@ void bind_comm(pybind11::module_& m) {
   m.def("comm_zero_fused_adam_rs", &py_zero_fused_adam_rs);
   m.attr("COMM_MAX_BLOCKS") = kCommMaxBlocks;
   m.attr("COMM_MAX_RANKS") = kMaxRanks;
+  m.attr("COMM_MAX_RANGES") = kMaxRanges;
 }

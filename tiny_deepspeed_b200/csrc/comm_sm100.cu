@@ -17,7 +17,9 @@
 namespace tds {
 
 constexpr int kCommThreads = 512;
-constexpr long long kSpinLimit = 20000000000LL;   // ~10 s of SM clocks
+// Flag waits are bounded by CommCtx::spin_limit (SM cycles; host default 600 s — long enough for rank-skewed host work such as
+// a rank-0 checkpoint or a first-step compile): on expiry the rank prints a diagnostic, raises the sticky error word
+// the host watchdog polls, and traps so the failure surfaces as a CUDA error instead of a silent hang.
 
 // ---- .sys-scope flag primitives -----------------------------------------------------------------------
 TDS_DEVICE uint32_t cas_release_sys(uint32_t* p, uint32_t cmp, uint32_t val) {
@@ -50,10 +52,10 @@ TDS_DEVICE void block_barrier(const CommCtx& c, int channel) {
     uint32_t* mine = flag_slot(c, c.rank, channel, blockIdx.x, peer);
     long long t0 = clock64();
     while (cas_release_sys(theirs, 0u, 1u) != 0u)
-      if (clock64() - t0 > kSpinLimit) spin_fail(c, "barrier(signal)", peer);
+      if (clock64() - t0 > c.spin_limit) spin_fail(c, "barrier(signal)", peer);
     t0 = clock64();
     while (cas_acquire_sys(mine, 1u, 0u) != 1u)
-      if (clock64() - t0 > kSpinLimit) spin_fail(c, "barrier(wait)", peer);
+      if (clock64() - t0 > c.spin_limit) spin_fail(c, "barrier(wait)", peer);
   }
   __syncthreads();
 }

@@ -55,7 +55,16 @@ struct GemmDev {
   int tma_store;  // epilogue goes registers -> swizzled smem -> TMA store (bf16 out, no accumulate, aligned)
   int dbg;      // TDS_GEMM_DBG bits (profiling only): 1 = no global stores, 2 = no MMA issue, 4 = no epilogue body
   uint32_t idesc;
+  long long* prof;   // per-CTA phase timestamps (16 x int64 per CTA), nullptr outside tools/gemm_timeline.py
 };
+
+// phase stamps of tools/gemm_timeline.py: one lane writes, only when a buffer was installed with gemm_set_prof()
+__device__ __forceinline__ void prof_stamp(const GemmDev& g, int slot) {
+  if (g.prof) g.prof[(long long)blockIdx.x * 16 + slot] = clock64();
+}
+__device__ __forceinline__ long long globaltimer_ns() {
+  long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
 
 template <int BN> struct Cfg {
   static constexpr int kStages = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
@@ -118,6 +127,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch();   // the next kernel may start its own prologue as soon as every CTA of this grid got here
+  if (g.prof && threadIdx.x == 0) {
+    uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g.prof[(long long)blockIdx.x * 16 + 0] = globaltimer_ns();
+    g.prof[(long long)blockIdx.x * 16 + 12] = smid;
+    prof_stamp(g, 1);
+  }
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tma_a);
@@ -142,6 +157,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const uint16_t cta_mask = (uint16_t)((1u << g.cm) - 1u);
   if (g.cm > 1) ptx::cluster_sync();   // peers' barriers exist before any multicast / remote commit targets them
   pdl_wait();     // everything above overlapped the previous kernel's tail; from here on we touch its outputs
+  if (threadIdx.x == 0) prof_stamp(g, 2);
 
   const int m_tiles = (g.M + BM - 1) / BM;
   const int n_tiles = (g.N + BN - 1) / BN;
@@ -160,8 +176,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int b1 = b / g.nb2, b2 = b % g.nb2;
         int kb0, kb1; tile_k_range<kBK>(g, m0, nkb, kb0, kb1);
         for (int kb = kb0; kb < kb1; ++kb) {
+          const bool ptrace = g.prof && blockIdx.x == 0 && t == 0 && kb >= kb0 + 6 && kb < kb0 + 10;
+          long long* ptr_ = ptrace ? g.prof + 148 * 16 + 64 + (kb - kb0 - 6) * 8 : nullptr;
+          if (ptrace) ptr_[0] = clock64();
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
+          if (ptrace) ptr_[1] = clock64();
           ptx::mbar_expect_tx(full_bar(stage), C::kABytes + C::kBBytes);
+          if (ptrace) ptr_[2] = clock64();
           const uint32_t a_dst = sA + stage * C::kABytes, b_dst = sB + stage * C::kBBytes;
           const int k0 = kb * kBK;
           // MN-major operands arrive as one box per 128-byte-wide MN group (64 bf16 / 32 fp32), bk k-rows each
@@ -196,6 +217,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                     n0 + 64 * i, k0 + (int)(cta_rank * krows), b2, b1, cta_mask);
             }
           }
+          if (ptrace) ptr_[3] = clock64();
+          if (g.prof) { if (kb == kb0 && t == (int)blockIdx.x) prof_stamp(g, 3); prof_stamp(g, 4); }
           if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -225,10 +248,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + as * BN;
       for (int kb = kb0; kb < kb1; ++kb) {
+        // fine-grained trace of the issuer loop (CTA 0, k-blocks 4..7 of its first tile): 8 stamps per k-block
+        const bool trace = g.prof && blockIdx.x == 0 && t == 0 && kb >= kb0 + 4 && kb < kb0 + 8 && lane == 0;
+        long long* tr = trace ? g.prof + 148 * 16 + (kb - kb0 - 4) * 8 : nullptr;
+        if (trace) tr[0] = clock64();
         ptx::mbar_wait(full_bar(stage), phase);
+        if (trace) tr[1] = clock64();
         ptx::tc_fence_after();
         if (lane == 0) {
+          if (g.prof) { if (kb == kb0 && t == (int)blockIdx.x) prof_stamp(g, 5); prof_stamp(g, 6); }
           const uint32_t a_s = sA + stage * C::kABytes, b_s = sB + stage * C::kBBytes;
+          if (trace) tr[2] = clock64();
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = ptx::make_smem_desc(a_s + k * a_adv, a_lbo, a_sbo, a_lt);
@@ -236,13 +266,18 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
             if (F32) ptx::mma_tf32_ss(d_tmem, da, db, g.idesc, acc);
             else if (!(g.dbg & 2)) ptx::mma_f16_ss(d_tmem, da, db, g.idesc, acc);
+            if (trace && k == 0) tr[3] = clock64();
           }
+          if (trace) tr[4] = clock64();
           // smem stage reusable once these MMAs retire (told to every CTA of the cluster when B is multicast)
           if (g.cm == 1) ptx::mma_commit(empty_bar(stage));
           else ptx::mma_commit_mc(empty_bar(stage), cta_mask);
           if (kb == kb1 - 1) ptx::mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
+          if (trace) tr[5] = clock64();
+          if (g.prof) prof_stamp(g, 7);
         }
         __syncwarp();
+        if (trace) tr[6] = clock64();
         if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
       }
     }
@@ -267,6 +302,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       ++local;
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
+      if (g.prof && warp == 2 && lane == 0) { if (t == (int)blockIdx.x) prof_stamp(g, 8); prof_stamp(g, 9); }
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < g.M;
       const long long d_off = (long long)b1 * g.dbs1 + (long long)b2 * g.dbs2 + (long long)m * g.ldd;
@@ -471,6 +507,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
+      if (g.prof && warp == 2 && lane == 0) prof_stamp(g, 10);
     }
     if (lane == 0) {
       if constexpr (RED) {
@@ -482,11 +519,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         ptx::bulk_wait_read<0>();     // staging smem must outlive the last TMA store's reads
       }
     }
+    if (g.prof && warp == 2 && lane == 0) prof_stamp(g, 11);
     __syncwarp();
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (g.prof && threadIdx.x == 0) { prof_stamp(g, 13); g.prof[(long long)blockIdx.x * 16 + 14] = globaltimer_ns(); }
   if (g.cm > 1) ptx::cluster_sync();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     ptx::tc_fence_after();
@@ -568,6 +607,12 @@ bool make_map_f32_2d(CUtensorMap* out, void* ptr, int64_t rows, int64_t cols, in
 }
 
 static int g_num_sms = 0;
+static long long* g_prof = nullptr;
+void gemm_set_prof(long long* buf) { g_prof = buf; }
+static int g_dbg = -1;       // TDS_GEMM_DBG bits; tools/gemm_harness.cu overrides them per run
+void gemm_set_debug(int bits) { g_dbg = bits; }
+static int g_variant = 0;    // experimental kernel variants compared by tools/gemm_harness.cu
+void gemm_set_variant(int v) { g_variant = v; }
 
 int gemm_num_configs() { return 4; }   // BN = 64, 128, 256, 192
 
@@ -672,8 +717,9 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   g.epi = p.aux ? p.epi : EPI_NONE; g.accumulate = p.accumulate ? 1 : 0; g.alpha = p.alpha;
   g.M = p.M; g.N = p.N; g.K = p.K; g.batch = p.batch; g.nb2 = nb2;
   g.a_mn = p.a.mn_major; g.b_mn = p.b.mn_major; g.tri = p.tri;
-  static const int dbg_env = getenv("TDS_GEMM_DBG") ? atoi(getenv("TDS_GEMM_DBG")) : 0;
-  g.dbg = dbg_env;
+  if (g_dbg < 0) g_dbg = getenv("TDS_GEMM_DBG") ? atoi(getenv("TDS_GEMM_DBG")) : 0;
+  g.dbg = g_dbg;
+  g.prof = g_prof;
   g.idesc = f32 ? make_idesc_tf32(BM, bn, p.a.mn_major, p.b.mn_major) : make_idesc_bf16(BM, bn, p.a.mn_major, p.b.mn_major);
   g.cm = cm;
   const long long tiles = (long long)((p.M + BM - 1) / BM) * ((p.N + bn - 1) / bn) * p.batch;

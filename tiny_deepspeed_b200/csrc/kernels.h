@@ -38,6 +38,7 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream);
 // its coverage (then call gemm_bf16).  Opt-in through TDS_GEMM_2CTA=1 in the binding.
 bool gemm2_bf16(const GemmParams& p, cudaStream_t stream);
 int gemm_num_configs();
+void gemm_set_prof(long long* buf);   // tools/gemm_timeline.py: per-CTA phase timestamps (nullptr = off)
 
 // ---- elementwise / reductions (elementwise.cu) ----------------------------------------------------
 void layernorm_fwd(const void* x, const void* w, const void* b, void* y, float* mean, float* rstd,

@@ -132,4 +132,7 @@ class TrainStep:
                 return loss
             self._capture()
         self.graph.replay()
+        # the captured step bumps the DEVICE step counter; mirror it so checkpoints / schedulers see the true step
+        self.optimizer.step_count += 1
+        self.optimizer._step_dev_for = self.optimizer.step_count
         return self._static_loss

@@ -12,7 +12,7 @@ class AdamW(Optimizer):
     reference's defects fixed: per-step ``t`` (not per tensor, :47-48,59), working ``amsgrad``
     (:50-53).  ``decoupled=True`` gives ``torch.optim.AdamW`` semantics."""
 
-    def __init__(self, named_parameters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2,
+    def __init__(self, named_parameters, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0,
                  amsgrad=False, maximize=False, decoupled=False):
         if lr < 0.0:
             raise ValueError(f"Invalid learning rate: {lr}")

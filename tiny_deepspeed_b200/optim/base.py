@@ -126,13 +126,38 @@ class Optimizer:
             self._zero_grad(p)
 
     # -- checkpointing (absent in the reference) ------------------------------------
+    def _policy_state(self):
+        """Native ZeRO + Adam keeps compact fp32 state inside the policy and creates it lazily at the first fused step;
+        checkpointing needs it (and its per-name views in ``self.state``) to exist before that."""
+        seen = set()
+        for p in self.parameters.values():
+            pol = getattr(p, "_tds_policy", None)
+            if pol is not None and id(pol) not in seen and getattr(pol, "is_native", False) and pol.owns_optimizer_state(self):
+                seen.add(id(pol))
+                pol._ensure_opt_state(self)
+
+    def sync_step_count(self):
+        """CUDA-graph replays advance only the device-resident counter: read it back so ``step_count`` is the truth."""
+        dev = getattr(self, "_step_dev", None)
+        if dev is not None:
+            self.step_count = int(dev.item())
+            self._step_dev_for = self.step_count
+        return self.step_count
+
     def state_dict(self):
+        self._policy_state()
+        self.sync_step_count()
         return {"step": self.step_count,
                 "state": {n: {k: v.detach().cpu() for k, v in st.items()} for n, st in self.state.items()},
                 "hyper": dict(self.hyper())}
 
     def load_state_dict(self, sd):
+        self._policy_state()
         self.step_count = int(sd["step"])
+        dev = getattr(self, "_step_dev", None)
+        if dev is not None:                       # a captured graph holds this tensor's address: update it in place
+            dev.fill_(self.step_count)
+            self._step_dev_for = self.step_count
         for n, st in sd["state"].items():
             if n in self.parameters and self.owned(n):
                 p = self.parameters[n]

@@ -458,6 +458,10 @@ class NativePolicy(CommPolicy):
             opt.state[n] = {"exp_avg": m[sl].view(self.shape[n]), "exp_avg_sq": v[sl].view(self.shape[n]),
                             "master": master[sl].view(self.shape[n])}
         ranges = [[self.goff[n], _pad(self.numel[n]), soff[n], self.poff[n]] for n in owned]
+        # every rank must launch the same number of (barrier-carrying) fused kernels: the rank owning most tensors decides
+        per_rank = [sum(1 for n in self.names if self._owner(n) == r) for r in range(self.world)]
+        max_ranges = int(ops.ext().COMM_MAX_RANGES)
+        self._min_launches = max(1, max((c + max_ranges - 1) // max_ranges for c in per_rank))
         self._opt_state = dict(master=master, m=m, v=v, ranges=ranges, owned=owned)
         return self._opt_state
 
@@ -484,7 +488,7 @@ class NativePolicy(CommPolicy):
                 ctx, gbuf, pbuf, rbuf, st["ranges_rs"], st["master"], st["m"], st["v"],
                 float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
                 bool(opt.decoupled), bool(opt.maximize), float(opt.grad_scale * self.scale),
-                self.mode != "zero3", 1)
+                self.mode != "zero3", 1, self._min_launches)
             ops.count_launch(int(launches))
             self.stats["fused_steps"] += 1
             for p in self.params.values():
@@ -497,7 +501,7 @@ class NativePolicy(CommPolicy):
             ctx, gbuf, pbuf, st["ranges"], st["master"], st["m"], st["v"],
             float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
             bool(opt.decoupled), bool(opt.maximize), float(opt.grad_scale * self.scale),
-            self.mode != "zero3", 1)
+            self.mode != "zero3", 1, self._min_launches)
         ops.count_launch(int(launches))
         self.stats["fused_steps"] += 1
         for p in self.params.values():

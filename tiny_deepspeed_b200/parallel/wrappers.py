@@ -107,6 +107,11 @@ class _ParallelWrapper(tnn.Module):
         self.module = model
 
         self.backend = self._pick_backend(backend)
+        # replicas first, sharding second: every rank still holds every tensor here, so each rank issues the SAME sequence
+        # of broadcasts (a ZeRO-3 policy replaces non-owned tensors with empty(0) right below — skipping a collective by
+        # local numel would desynchronise NCCL)
+        if broadcast_init and self.world_size > 1:
+            self._broadcast_initial()
         if self.backend == "native":
             from .native_policy import NativePolicy
             self.policy = NativePolicy(self.mode, model, table=param_part_table, group=group,
@@ -128,8 +133,6 @@ class _ParallelWrapper(tnn.Module):
             if not hasattr(p, "_tds_shape"):
                 p._tds_shape = tuple(p.shape)
         self.set_rank_id()
-        if broadcast_init and self.world_size > 1:
-            self._broadcast_initial()
         if self.mode == "zero3" and self.world_size > 1 and self.backend == "dist":
             shard_parameters_(model, param_part_table, self.rank)
 
@@ -157,8 +160,8 @@ class _ParallelWrapper(tnn.Module):
         The reference never does this."""
         with torch.no_grad():
             for name, p in self.module.named_parameters():
-                if p.numel() == 0:
-                    continue
+                if p.device.type == "meta":
+                    continue      # cannot happen after materialize_ (which also switches broadcast_init off)
                 src = 0 if self.mode == "ddp" else self.param_part_table[name]
                 if self.group is not None:
                     src = dist.get_global_rank(self.group, src)

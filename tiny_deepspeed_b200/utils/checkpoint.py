@@ -31,6 +31,10 @@ def save_checkpoint(directory: str, model, optimizer=None, *, table: Optional[Di
     tmp = path + ".tmp"
     torch.save(payload, tmp)
     os.replace(tmp, path)
+    # collective exit: no rank runs ahead into the next step (whose device-side flag waits are bounded) while a peer is
+    # still serialising its shard
+    if world > 1:
+        dist.barrier()
     return path
 
 

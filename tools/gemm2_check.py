@@ -38,7 +38,8 @@ def bench(fn, n=20):
 def main():
     dev = "cuda"
     on = os.environ.get("TDS_GEMM_2CTA", "0") == "1"
-    print(f"pair kernel {'ON' if on else 'off'}")
+    ops.ext().set_gemm_pair(1 if on else 0)
+    print(f"pair kernel {'ON' if on else 'off'}", flush=True)
     worst = 0.0
     for (M, N, K) in SHAPES:
         for a_mn, b_mn in [(False, False), (False, True), (True, True)]:
@@ -54,7 +55,7 @@ def main():
             r = rel(got, ref)
             worst = max(worst, r)
             us = bench(lambda: ops.gemm(a, b, a_mn=a_mn, b_mn=b_mn, bias=bias))
-            print(f"M{M} N{N} K{K} a_mn={int(a_mn)} b_mn={int(b_mn)}  rel {r:.2e}  {us:8.1f} us  {2 * M * N * K / us / 1e6:7.1f} TFLOP/s")
+            print(f"M{M} N{N} K{K} a_mn={int(a_mn)} b_mn={int(b_mn)}  rel {r:.2e}  {us:8.1f} us  {2 * M * N * K / us / 1e6:7.1f} TFLOP/s", flush=True)
     print("worst rel", worst)
     if on and "--no-baseline" not in sys.argv:
         env = dict(os.environ, TDS_GEMM_2CTA="0")
