@@ -36,7 +36,8 @@ namespace tds {
 constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // one 128-byte swizzle row of bf16
 constexpr int UK = 16;        // UMMA K for 16-bit inputs
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;        // single pipeline: producer, issuer, 4 epilogue warps
+constexpr int kThreadsDual = 256;    // dual pipeline: 2 x (producer, issuer), 4 epilogue warps
 constexpr uint32_t kStageBufBytes = 4096;   // one 32-row x 64-col bf16 slab, SWIZZLE_128B
 
 enum { EPI_NONE = 0, EPI_GELU_SAVE = 1, EPI_GELU_BWD = 2, EPI_RESIDUAL = 3 };
@@ -72,6 +73,7 @@ template <int BN> struct Cfg {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kSmem = kStages * (kABytes + kBBytes) + 4 * 2 * 4096 /*epilogue staging*/ + 1024 /*align*/ + 256 /*barriers*/;
   static constexpr int kTmemCols = BN == 64 ? 128 : (BN == 128 ? 256 : 512);   // power of two >= 2 * BN
+  static constexpr int kTmemColsDual = BN == 64 ? 256 : 512;                   // 2 accumulator stages x 2 half-K accumulators
 };
 
 template <int KB>
@@ -100,12 +102,22 @@ __device__ __forceinline__ float ld1_any(const void* base, long long idx, int f3
 //       destination by the TMA (cp.reduce.async.bulk.tensor .add) instead of stored; the destination may be ANOTHER rank's
 //       copy of a symmetric gradient shard, so the dW GEMM of every rank accumulates straight into the owner over NVLink,
 //       tile by tile, while the GEMM is still running.  Compile-time so the default instantiations stay byte-identical.
-template <int BN, bool F32, bool RED>
-__global__ void __launch_bounds__(kThreads, 1)
+// DUAL = two independent half-K pipelines inside the CTA (BN <= 128 only): (producer warp 0, issuer warp 1) stream the even
+//       k-blocks through the lower half of the smem ring into accumulator D0, (warp 2, warp 3) the odd k-blocks through the
+//       upper half into D1, and the epilogue adds D0 + D1.  Measured with tools/mma_probe.cu: ONE thread can issue a
+//       tcgen05.mma only every ~80-100 cycles whatever its shape, i.e. 128 x 64/128 x 16 MMAs (32/64 cycles of tensor-pipe
+//       work) leave the pipe idle most of the time; two issuing threads on disjoint accumulators reach the pipe's own rate
+//       (49 / 65 cycles per MMA for N = 64 / 128).  The same holds for the single TMA-issuing thread (~340 cycles per k-block).
+template <int BN, bool F32, bool RED, bool DUAL>
+__global__ void __launch_bounds__(DUAL ? kThreadsDual : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
             const __grid_constant__ GemmDev g) {
   using C = Cfg<BN>;
+  constexpr int kHalves = DUAL ? 2 : 1;
+  constexpr int kSH = C::kStages / kHalves;            // ring stages per pipeline
+  constexpr int kAccCols = kHalves * BN;               // TMEM columns of one accumulator stage
+  constexpr int kEpiWarp0 = DUAL ? 4 : 2;              // first epilogue warp
   constexpr int kBK = F32 ? 32 : BK;     // K elements per stage = one 128-byte row
   constexpr int kGrp = F32 ? 32 : 64;    // MN elements per 128-byte row of an MN-major operand
   extern __shared__ uint8_t smem_raw[];
@@ -125,7 +137,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // shfl result = provably warp-uniform: role branches below are uniform branches and per-role state lives in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   pdl_launch();   // the next kernel may start its own prologue as soon as every CTA of this grid got here
   if (g.prof && threadIdx.x == 0) {
     uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
@@ -134,19 +147,19 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     prof_stamp(g, 1);
   }
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
     if (g.tma_store) ptx::prefetch_tmap(&tma_d);
     // a smem stage is refilled by EVERY CTA of the cluster (B slices are multicast), so it is free only when all
     // cm MMA issuers have released it
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (uint32_t)g.cm); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), 1); ptx::mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), kHalves); ptx::mbar_init(tempty_bar(s), 4); }
     for (int w = 0; w < 4; ++w) ptx::mbar_init(aux_bar(w), 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, C::kTmemCols);
+    ptx::tmem_alloc(tmem_slot, DUAL ? C::kTmemColsDual : C::kTmemCols);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -165,68 +178,71 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int total_tiles = tiles_per_batch * g.batch;
   const int nkb = (g.K + kBK - 1) / kBK;
 
-  if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+  // half-K pipeline this warp belongs to (DUAL): warps 0/1 = half 0, warps 2/3 = half 1
+  const int half = DUAL ? (warp >> 1) & 1 : 0;
+  const bool is_producer = DUAL ? (warp == 0 || warp == 2) : warp == 0;
+  const bool is_issuer = DUAL ? (warp == 1 || warp == 3) : warp == 1;
+  const int s0 = half * kSH;                           // this pipeline's slice of the smem ring
+
+  if (is_producer) {
+    // ===================== TMA producer (one elected thread runs the whole loop) =====================
+    if (ptx::elect_one()) {
       int stage = 0; uint32_t phase = 0;
+      bool first = true;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         const int b = t / tiles_per_batch, r = t % tiles_per_batch;
         const int m0 = (r % m_tiles) * BM, n0 = (r / m_tiles) * BN;   // m fastest: neighbours share the B tile in L2
         if (g.tri == 1 && n0 > m0 + BM - 1) continue;
         const int b1 = b / g.nb2, b2 = b % g.nb2;
         int kb0, kb1; tile_k_range<kBK>(g, m0, nkb, kb0, kb1);
-        for (int kb = kb0; kb < kb1; ++kb) {
-          const bool ptrace = g.prof && blockIdx.x == 0 && t == 0 && kb >= kb0 + 6 && kb < kb0 + 10;
-          long long* ptr_ = ptrace ? g.prof + 148 * 16 + 64 + (kb - kb0 - 6) * 8 : nullptr;
-          if (ptrace) ptr_[0] = clock64();
-          ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
-          if (ptrace) ptr_[1] = clock64();
-          ptx::mbar_expect_tx(full_bar(stage), C::kABytes + C::kBBytes);
-          if (ptrace) ptr_[2] = clock64();
-          const uint32_t a_dst = sA + stage * C::kABytes, b_dst = sB + stage * C::kBBytes;
+        for (int kb = kb0 + half; kb < kb1; kb += kHalves) {
+          const int sg = s0 + stage;
+          ptx::mbar_wait_conv(empty_bar(sg), phase ^ 1u);
+          ptx::mbar_expect_tx(full_bar(sg), C::kABytes + C::kBBytes);
+          const uint32_t a_dst = sA + sg * C::kABytes, b_dst = sB + sg * C::kBBytes;
           const int k0 = kb * kBK;
           // MN-major operands arrive as one box per 128-byte-wide MN group (64 bf16 / 32 fp32), bk k-rows each
           constexpr uint32_t grp_bytes = (uint32_t)kBK * 128u;
           if (!g.a_mn) {
-            ptx::tma_load_4d(a_dst, &tma_a, full_bar(stage), k0, m0, b2, b1);
+            ptx::tma_load_4d(a_dst, &tma_a, full_bar(sg), k0, m0, b2, b1);
           } else {
 #pragma unroll
             for (int i = 0; i < BM / kGrp; ++i)
-              ptx::tma_load_4d(a_dst + i * grp_bytes, &tma_a, full_bar(stage), m0 + kGrp * i, k0, b2, b1);
+              ptx::tma_load_4d(a_dst + i * grp_bytes, &tma_a, full_bar(sg), m0 + kGrp * i, k0, b2, b1);
           }
           if (g.cm == 1) {
             if (!g.b_mn) {
-              ptx::tma_load_4d(b_dst, &tma_b, full_bar(stage), k0, n0, b2, b1);
+              ptx::tma_load_4d(b_dst, &tma_b, full_bar(sg), k0, n0, b2, b1);
             } else {
 #pragma unroll
               for (int i = 0; i < BN / kGrp; ++i)
-                ptx::tma_load_4d(b_dst + i * grp_bytes, &tma_b, full_bar(stage), n0 + kGrp * i, k0, b2, b1);
+                ptx::tma_load_4d(b_dst + i * grp_bytes, &tma_b, full_bar(sg), n0 + kGrp * i, k0, b2, b1);
             }
           } else {   // (bf16 only: pick_cluster never forms clusters for fp32 operands)
             // The cm CTAs of the cluster work on cm consecutive M tiles of the SAME N tile: each fetches 1/cm of
             // the B tile and the TMA multicasts it into every CTA's smem (one L2 / NVLink read per cluster).
             if (!g.b_mn) {
               const uint32_t rows = BN / g.cm;
-              ptx::tma_load_4d_mc(b_dst + cta_rank * rows * 128u, &tma_b, full_bar(stage), k0, n0 + (int)(cta_rank * rows),
+              ptx::tma_load_4d_mc(b_dst + cta_rank * rows * 128u, &tma_b, full_bar(sg), k0, n0 + (int)(cta_rank * rows),
                                   b2, b1, cta_mask);
             } else {
               const uint32_t krows = BK / g.cm;
 #pragma unroll
               for (int i = 0; i < BN / 64; ++i)
-                ptx::tma_load_4d_mc(b_dst + i * (BK * 128) + cta_rank * krows * 128u, &tma_b, full_bar(stage),
+                ptx::tma_load_4d_mc(b_dst + i * (BK * 128) + cta_rank * krows * 128u, &tma_b, full_bar(sg),
                                     n0 + 64 * i, k0 + (int)(cta_rank * krows), b2, b1, cta_mask);
             }
           }
-          if (ptrace) ptr_[3] = clock64();
-          if (g.prof) { if (kb == kb0 && t == (int)blockIdx.x) prof_stamp(g, 3); prof_stamp(g, 4); }
-          if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+          if (g.prof && half == 0) { if (first) { prof_stamp(g, 3); first = false; } prof_stamp(g, 4); }
+          if (++stage == kSH) { stage = 0; phase ^= 1u; }
         }
       }
     }
-  } else if (warp == 1) {
-    // ===================== MMA issuer =====================
+  } else if (is_issuer) {
+    // ===================== MMA issuer (converged warp; one elected lane issues) =====================
     int stage = 0; uint32_t phase = 0;
     int local = 0;
+    bool first = true;
     // descriptor strides: K-major: SBO = 1024 (8 rows x 128 B), per-UMMA_K advance 32 B;
     //                     MN-major: LBO = BK*128 (next 64-wide MN group), SBO = 1024, advance 16 k-rows = 2048 B
     //                     (fp32/TF32: UMMA K = 8 -> 32 B per k-step K-major as well, 8 k-rows = 1024 B MN-major)
@@ -244,41 +260,47 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       ++local;
-      ptx::mbar_wait(tempty_bar(as), aphase ^ 1u);
+      ptx::mbar_wait_conv(tempty_bar(as), aphase ^ 1u);
       ptx::tc_fence_after();
-      const uint32_t d_tmem = tmem_base + as * BN;
-      for (int kb = kb0; kb < kb1; ++kb) {
-        // fine-grained trace of the issuer loop (CTA 0, k-blocks 4..7 of its first tile): 8 stamps per k-block
-        const bool trace = g.prof && blockIdx.x == 0 && t == 0 && kb >= kb0 + 4 && kb < kb0 + 8 && lane == 0;
-        long long* tr = trace ? g.prof + 148 * 16 + (kb - kb0 - 4) * 8 : nullptr;
-        if (trace) tr[0] = clock64();
-        ptx::mbar_wait(full_bar(stage), phase);
-        if (trace) tr[1] = clock64();
+      const uint32_t d_tmem = tmem_base + as * kAccCols + half * BN;
+      if (DUAL && kb0 + half >= kb1) {
+        // this pipeline has no k-block in the tile (a one-k-block causal range): the epilogue still expects both arrivals
+        if (ptx::elect_one()) ptx::mbar_arrive(tfull_bar(as));
+        __syncwarp();
+        continue;
+      }
+      for (int kb = kb0 + half; kb < kb1; kb += kHalves) {
+        const int sg = s0 + stage;
+        // fine-grained trace of the issuer loop (CTA 0, its first tile, this pipeline's k-blocks 2..5)
+        const int it = (kb - kb0) / kHalves;
+        const bool trace = g.prof && blockIdx.x == 0 && t == 0 && half == 0 && it >= 2 && it < 6;
+        long long* tr = trace ? g.prof + 148 * 16 + (it - 2) * 8 : nullptr;
+        if (trace && lane == 0) tr[0] = clock64();
+        ptx::mbar_wait_conv(full_bar(sg), phase);         // all lanes poll: the warp stays converged
         ptx::tc_fence_after();
-        if (lane == 0) {
-          if (g.prof) { if (kb == kb0 && t == (int)blockIdx.x) prof_stamp(g, 5); prof_stamp(g, 6); }
-          const uint32_t a_s = sA + stage * C::kABytes, b_s = sB + stage * C::kBBytes;
-          if (trace) tr[2] = clock64();
+        if (trace && lane == 0) tr[1] = clock64();
+        if (ptx::elect_one()) {
+          const uint32_t a_s = sA + sg * C::kABytes, b_s = sB + sg * C::kBBytes;
 #pragma unroll
           for (int k = 0; k < BK / UK; ++k) {
             const uint64_t da = ptx::make_smem_desc(a_s + k * a_adv, a_lbo, a_sbo, a_lt);
             const uint64_t db = ptx::make_smem_desc(b_s + k * b_adv, b_lbo, b_sbo, b_lt);
-            const uint32_t acc = (kb > kb0 || k > 0) ? 1u : 0u;
+            const uint32_t acc = (kb > kb0 + half || k > 0) ? 1u : 0u;
             if (F32) ptx::mma_tf32_ss(d_tmem, da, db, g.idesc, acc);
             else if (!(g.dbg & 2)) ptx::mma_f16_ss(d_tmem, da, db, g.idesc, acc);
-            if (trace && k == 0) tr[3] = clock64();
           }
-          if (trace) tr[4] = clock64();
           // smem stage reusable once these MMAs retire (told to every CTA of the cluster when B is multicast)
-          if (g.cm == 1) ptx::mma_commit(empty_bar(stage));
-          else ptx::mma_commit_mc(empty_bar(stage), cta_mask);
-          if (kb == kb1 - 1) ptx::mma_commit(tfull_bar(as));  // accumulator complete -> epilogue
-          if (trace) tr[5] = clock64();
-          if (g.prof) prof_stamp(g, 7);
+          if (g.cm == 1) ptx::mma_commit(empty_bar(sg));
+          else ptx::mma_commit_mc(empty_bar(sg), cta_mask);
+          if (kb + kHalves >= kb1) ptx::mma_commit(tfull_bar(as));   // this pipeline's accumulator complete -> epilogue
         }
         __syncwarp();
-        if (trace) tr[6] = clock64();
-        if (++stage == C::kStages) { stage = 0; phase ^= 1u; }
+        if (g.prof && lane == 0 && half == 0) {
+          if (first) { prof_stamp(g, 5); first = false; }
+          prof_stamp(g, 6);
+          if (trace) tr[2] = clock64();
+        }
+        if (++stage == kSH) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -302,11 +324,26 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       ++local;
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
-      if (g.prof && warp == 2 && lane == 0) { if (t == (int)blockIdx.x) prof_stamp(g, 8); prof_stamp(g, 9); }
+      if (g.prof && warp == kEpiWarp0 && lane == 0) { if (t == (int)blockIdx.x) prof_stamp(g, 8); prof_stamp(g, 9); }
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < g.M;
       const long long d_off = (long long)b1 * g.dbs1 + (long long)b2 * g.dbs2 + (long long)m * g.ldd;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * BN;
+      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccCols;
+      // DUAL: D = D0 + D1 (even + odd k-blocks); D1 is untouched when the tile's K range holds a single k-block
+      bool two = false;
+      if (DUAL) { int kb0, kb1; tile_k_range<kBK>(g, m0, nkb, kb0, kb1); two = kb0 + 1 < kb1; }
+      auto ld_acc = [&](uint32_t col, uint32_t (&raw)[32]) {
+        ptx::tmem_ld_32x32(t_row + col, raw);
+        if (DUAL && two) {
+          uint32_t hi[32];
+          ptx::tmem_ld_32x32(t_row + BN + col, hi);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(hi[j]));
+        } else {
+          ptx::tmem_ld_wait();
+        }
+      };
       if constexpr (RED) {
         // ---- reduce path: 32 x 32 fp32 slabs (128-byte rows, SWIZZLE_128B) -> TMA reduce-add into (peer) global memory ----
 #pragma unroll 1
@@ -318,8 +355,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (lane == 0) ptx::bulk_wait_read<1>();
           __syncwarp();
           uint32_t raw[32];
-          ptx::tmem_ld_32x32(t_row + slab * 32, raw);
-          ptx::tmem_ld_wait();
+          ld_acc(slab * 32, raw);
 #pragma unroll
           for (int c16 = 0; c16 < 8; ++c16) {
             const float4 v = make_float4(__uint_as_float(raw[c16 * 4]) * g.alpha, __uint_as_float(raw[c16 * 4 + 1]) * g.alpha,
@@ -356,8 +392,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
             uint32_t raw[32];
-            ptx::tmem_ld_32x32(t_row + slab * 64 + half * 32, raw);
-            ptx::tmem_ld_wait();
+            ld_acc(slab * 64 + half * 32, raw);
             const int nb = ns + half * 32;
             float v[32];
 #pragma unroll
@@ -404,8 +439,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll 1
         for (int c = 0; c < ((g.dbg & 4) ? 0 : BN / 32); ++c) {
           uint32_t raw[32];
-          ptx::tmem_ld_32x32(t_row + c * 32, raw);
-          ptx::tmem_ld_wait();
+          ld_acc(c * 32, raw);
           const int nb = n0 + c * 32;
           if (row_ok && nb < g.N && !(g.dbg & 1)) {
             float v[32];
@@ -507,7 +541,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
-      if (g.prof && warp == 2 && lane == 0) prof_stamp(g, 10);
+      if (g.prof && warp == kEpiWarp0 && lane == 0) prof_stamp(g, 10);
     }
     if (lane == 0) {
       if constexpr (RED) {
@@ -519,7 +553,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         ptx::bulk_wait_read<0>();     // staging smem must outlive the last TMA store's reads
       }
     }
-    if (g.prof && warp == 2 && lane == 0) prof_stamp(g, 11);
+    if (g.prof && warp == kEpiWarp0 && lane == 0) prof_stamp(g, 11);
     __syncwarp();
   }
 
@@ -529,7 +563,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (g.cm > 1) ptx::cluster_sync();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, C::kTmemCols);
+    ptx::tmem_dealloc(tmem_base, DUAL ? C::kTmemColsDual : C::kTmemCols);
   }
 }
 
@@ -641,22 +675,22 @@ static int max_clusters(int cm) {
   at[0].val.clusterDim.x = cm; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false, false, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
   cache[cm] = n;
   return n;
 }
 
-template <int BN, bool F32, bool RED = false>
+template <int BN, bool F32, bool RED = false, bool DUAL = false>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                    const GemmDev& g, int tiles, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_kernel<BN, F32, RED>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+    cudaFuncSetAttribute(gemm_kernel<BN, F32, RED, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
     attr_done = true;
   }
   if (g.cm == 1) {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    launch_k(gemm_kernel<BN, F32, RED>, dim3(grid), dim3(kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
+    launch_k(gemm_kernel<BN, F32, RED, DUAL>, dim3(grid), dim3(DUAL ? kThreadsDual : kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
     return;
   }
   // cluster launch: cm consecutive CTAs = cm consecutive M tiles of one N tile; grid is a whole number of clusters
@@ -665,7 +699,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   if (clusters > cap) clusters = cap;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * g.cm);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(DUAL ? kThreadsDual : kThreads);
   cfg.dynamicSmemBytes = Cfg<BN>::kSmem;
   cfg.stream = s;
   cudaLaunchAttribute at[2];
@@ -674,7 +708,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32, RED>, ta, tb, td, tx, g);
+  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32, RED, DUAL>, ta, tb, td, tx, g);
 }
 
 // cluster size along M: B-tile multicast divides L2->SM (or NVLink, for a ZeRO-3 peer weight) operand traffic by cm
@@ -747,9 +781,13 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
     }
     g.tma_store = ok ? 1 : 0;
   }
+  // two half-K pipelines per CTA whenever the MMA is narrow enough to be issue-bound (BN <= 128, bf16); TDS_GEMM_DUAL=0 /
+  // gemm_set_variant(1) keeps the single pipeline for A/B measurements
+  static const int dual_env = getenv("TDS_GEMM_DUAL") ? atoi(getenv("TDS_GEMM_DUAL")) : 1;
+  const bool dual = dual_env && g_variant != 1 && !f32 && bn <= 128;
   if (p.reduce_out) {
-    if (cfg == 0) launch<64, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
-    else if (cfg == 1) launch<128, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    if (cfg == 0) { if (dual) launch<64, false, true, true>(ta, tb, td, tx, g, (int)tiles, stream); else launch<64, false, true>(ta, tb, td, tx, g, (int)tiles, stream); }
+    else if (cfg == 1) { if (dual) launch<128, false, true, true>(ta, tb, td, tx, g, (int)tiles, stream); else launch<128, false, true>(ta, tb, td, tx, g, (int)tiles, stream); }
     else if (cfg == 2) launch<256, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
     else launch<192, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
   } else if (f32) {
@@ -758,8 +796,8 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
     else if (cfg == 2) launch<256, true>(ta, tb, td, tx, g, (int)tiles, stream);
     else launch<192, true>(ta, tb, td, tx, g, (int)tiles, stream);
   } else {
-    if (cfg == 0) launch<64, false>(ta, tb, td, tx, g, (int)tiles, stream);
-    else if (cfg == 1) launch<128, false>(ta, tb, td, tx, g, (int)tiles, stream);
+    if (cfg == 0) { if (dual) launch<64, false, false, true>(ta, tb, td, tx, g, (int)tiles, stream); else launch<64, false>(ta, tb, td, tx, g, (int)tiles, stream); }
+    else if (cfg == 1) { if (dual) launch<128, false, false, true>(ta, tb, td, tx, g, (int)tiles, stream); else launch<128, false>(ta, tb, td, tx, g, (int)tiles, stream); }
     else if (cfg == 2) launch<256, false>(ta, tb, td, tx, g, (int)tiles, stream);
     else launch<192, false>(ta, tb, td, tx, g, (int)tiles, stream);
   }

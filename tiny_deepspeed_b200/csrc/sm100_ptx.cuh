@@ -45,6 +45,38 @@ TDS_PTX void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// Wait as ONE asm block: the spin loop is invisible to the compiler, so a warp whose lanes all call it stays converged and
+// warp-uniform values (stage, phase, descriptors) stay in uniform registers.  With the C++-level loop above, every
+// tcgen05.mma / TMA issue that followed under `if (lane == 0)` was compiled into an ELECT + R2UR + BRA.U.ANY sequence
+// (~70-120 cycles per instruction, measured with tools/gemm_harness trace) and the single issuing thread became the
+// bottleneck of every M = 1024 GEMM.  Bounded like mbar_wait: ~2^22 polls with a 1 ms suspend hint, then trap.
+TDS_PTX void mbar_wait_conv(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 1000000;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 4194304;\n\t"
+      "@p bra WAIT_LOOP;\n\t"
+      "trap;\n\t"
+      "WAIT_DONE:\n\t}"
+      ::"r"(bar), "r"(parity)
+      : "memory");
+}
+// Exactly one lane of the (converged) warp gets `true`; the compiler knows the guarded region is single-threaded, so
+// uniform-datapath instructions (UTMALDG / UTCHMMA / UTCBAR / UTMASTG) are emitted straight, without an election loop.
+TDS_PTX bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- TMA ----------------------------------------------------------------------------------------------
 TDS_PTX void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

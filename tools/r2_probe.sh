@@ -1,5 +1,5 @@
 #!/usr/bin/env bash
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
-timeout 200 tools/tma_probe > gpurun_out/r2_tma_probe.log 2>&1; echo "probe rc=$?"
-cat gpurun_out/r2_tma_probe.log
+timeout 100 tools/${1:-tma_probe} > gpurun_out/r2_${1:-tma_probe}.log 2>&1; echo "probe rc=$?"
+cat gpurun_out/r2_${1:-tma_probe}.log
