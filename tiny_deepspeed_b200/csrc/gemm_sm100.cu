@@ -59,9 +59,16 @@ struct GemmDev {
   long long* prof;   // per-CTA phase timestamps (16 x int64 per CTA), nullptr outside tools/gemm_timeline.py
 };
 
-// phase stamps of tools/gemm_timeline.py: one lane writes, only when a buffer was installed with gemm_set_prof()
-__device__ __forceinline__ void prof_stamp(const GemmDev& g, int slot) {
-  if (g.prof) g.prof[(long long)blockIdx.x * 16 + slot] = clock64();
+// Phase stamps / debug bits exist only in builds with -DTDS_GEMM_PROF (tools/build_harness.sh): the production kernels carry
+// none of that code — at M = 1024 the prologue and epilogue run once per CTA out of a cold instruction cache, so every
+// kilobyte of dead branches costs cycles (profiles/r2_gemm_issue_path.md).
+#ifdef TDS_GEMM_PROF
+constexpr bool kProf = true;
+#else
+constexpr bool kProf = false;
+#endif
+__device__ __forceinline__ void prof_stamp(long long* prof, int slot) {
+  if (prof) prof[(long long)blockIdx.x * 16 + slot] = clock64();
 }
 __device__ __forceinline__ long long globaltimer_ns() {
   long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
@@ -108,12 +115,18 @@ __device__ __forceinline__ float ld1_any(const void* base, long long idx, int f3
 //       tcgen05.mma only every ~80-100 cycles whatever its shape, i.e. 128 x 64/128 x 16 MMAs (32/64 cycles of tensor-pipe
 //       work) leave the pipe idle most of the time; two issuing threads on disjoint accumulators reach the pipe's own rate
 //       (49 / 65 cycles per MMA for N = 64 / 128).  The same holds for the single TMA-issuing thread (~340 cycles per k-block).
-template <int BN, bool F32, bool RED, bool DUAL>
+// EPI  = epilogue functor fixed at compile time (EPI_*), or -1: read g.epi at run time (generic instantiations)
+// FAST = the output goes registers -> swizzled smem -> TMA store and nothing else is compiled in (bf16 out, aligned, no
+//        accumulate: every GEMM of the bf16 training step); the generic instantiations keep the direct-store paths
+template <int BN, bool F32, bool RED, bool DUAL, int EPI, bool FAST>
 __global__ void __launch_bounds__(DUAL ? kThreadsDual : kThreads, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
             const __grid_constant__ GemmDev g) {
   using C = Cfg<BN>;
+  long long* const prof = kProf ? g.prof : nullptr;     // compile-time nullptr in production builds
+  const int dbg = kProf ? g.dbg : 0;
+  const int epi = EPI >= 0 ? EPI : g.epi;
   constexpr int kHalves = DUAL ? 2 : 1;
   constexpr int kSH = C::kStages / kHalves;            // ring stages per pipeline
   constexpr int kAccCols = kHalves * BN;               // TMEM columns of one accumulator stage
@@ -140,17 +153,17 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   // shfl result = provably warp-uniform: role branches below are uniform branches and per-role state lives in uniform registers
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   pdl_launch();   // the next kernel may start its own prologue as soon as every CTA of this grid got here
-  if (g.prof && threadIdx.x == 0) {
+  if (prof && threadIdx.x == 0) {
     uint32_t smid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    g.prof[(long long)blockIdx.x * 16 + 0] = globaltimer_ns();
-    g.prof[(long long)blockIdx.x * 16 + 12] = smid;
-    prof_stamp(g, 1);
+    prof[(long long)blockIdx.x * 16 + 0] = globaltimer_ns();
+    prof[(long long)blockIdx.x * 16 + 12] = smid;
+    prof_stamp(prof, 1);
   }
 
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tma_a);
     ptx::prefetch_tmap(&tma_b);
-    if (g.tma_store) ptx::prefetch_tmap(&tma_d);
+    if (FAST || g.tma_store) ptx::prefetch_tmap(&tma_d);
     // a smem stage is refilled by EVERY CTA of the cluster (B slices are multicast), so it is free only when all
     // cm MMA issuers have released it
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (uint32_t)g.cm); }
@@ -170,7 +183,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const uint16_t cta_mask = (uint16_t)((1u << g.cm) - 1u);
   if (g.cm > 1) ptx::cluster_sync();   // peers' barriers exist before any multicast / remote commit targets them
   pdl_wait();     // everything above overlapped the previous kernel's tail; from here on we touch its outputs
-  if (threadIdx.x == 0) prof_stamp(g, 2);
+  if (threadIdx.x == 0) prof_stamp(prof, 2);
 
   const int m_tiles = (g.M + BM - 1) / BM;
   const int n_tiles = (g.N + BN - 1) / BN;
@@ -233,7 +246,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                                     n0 + 64 * i, k0 + (int)(cta_rank * krows), b2, b1, cta_mask);
             }
           }
-          if (g.prof && half == 0) { if (first) { prof_stamp(g, 3); first = false; } prof_stamp(g, 4); }
+          if (prof && half == 0) { if (first) { prof_stamp(prof, 3); first = false; } prof_stamp(prof, 4); }
           if (++stage == kSH) { stage = 0; phase ^= 1u; }
         }
       }
@@ -273,8 +286,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         const int sg = s0 + stage;
         // fine-grained trace of the issuer loop (CTA 0, its first tile, this pipeline's k-blocks 2..5)
         const int it = (kb - kb0) / kHalves;
-        const bool trace = g.prof && blockIdx.x == 0 && t == 0 && half == 0 && it >= 2 && it < 6;
-        long long* tr = trace ? g.prof + 148 * 16 + (it - 2) * 8 : nullptr;
+        const bool trace = prof && blockIdx.x == 0 && t == 0 && half == 0 && it >= 2 && it < 6;
+        long long* tr = trace ? prof + 148 * 16 + (it - 2) * 8 : nullptr;
         if (trace && lane == 0) tr[0] = clock64();
         ptx::mbar_wait_conv(full_bar(sg), phase);         // all lanes poll: the warp stays converged
         ptx::tc_fence_after();
@@ -287,7 +300,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             const uint64_t db = ptx::make_smem_desc(b_s + k * b_adv, b_lbo, b_sbo, b_lt);
             const uint32_t acc = (kb > kb0 + half || k > 0) ? 1u : 0u;
             if (F32) ptx::mma_tf32_ss(d_tmem, da, db, g.idesc, acc);
-            else if (!(g.dbg & 2)) ptx::mma_f16_ss(d_tmem, da, db, g.idesc, acc);
+            else if (!(dbg & 2)) ptx::mma_f16_ss(d_tmem, da, db, g.idesc, acc);
           }
           // smem stage reusable once these MMAs retire (told to every CTA of the cluster when B is multicast)
           if (g.cm == 1) ptx::mma_commit(empty_bar(sg));
@@ -295,9 +308,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           if (kb + kHalves >= kb1) ptx::mma_commit(tfull_bar(as));   // this pipeline's accumulator complete -> epilogue
         }
         __syncwarp();
-        if (g.prof && lane == 0 && half == 0) {
-          if (first) { prof_stamp(g, 5); first = false; }
-          prof_stamp(g, 6);
+        if (prof && lane == 0 && half == 0) {
+          if (first) { prof_stamp(prof, 5); first = false; }
+          prof_stamp(prof, 6);
           if (trace) tr[2] = clock64();
         }
         if (++stage == kSH) { stage = 0; phase ^= 1u; }
@@ -309,8 +322,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     int local = 0;
     uint32_t sbuf_toggle = 0;
     const uint32_t my_stage0 = sStage + (uint32_t)q * 2u * kStageBufBytes;   // two 4 KB staging buffers per warp
-    const bool gelu_save = g.epi == EPI_GELU_SAVE;
-    const bool aux_in = g.aux_tma && (g.epi == EPI_GELU_BWD || g.epi == EPI_RESIDUAL);   // aux tile arrives by TMA
+    const bool gelu_save = epi == EPI_GELU_SAVE;
+    const bool aux_in = g.aux_tma && (epi == EPI_GELU_BWD || epi == EPI_RESIDUAL);   // aux tile arrives by TMA
     uint32_t aux_phase = 0;
     const bool vec_ok = (g.N % 8 == 0) && (g.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(g.d) & 15) == 0) &&
                         (g.aux == nullptr || (g.ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0));
@@ -324,7 +337,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       ++local;
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
-      if (g.prof && warp == kEpiWarp0 && lane == 0) { if (t == (int)blockIdx.x) prof_stamp(g, 8); prof_stamp(g, 9); }
+      if (prof && warp == kEpiWarp0 && lane == 0) { if (t == (int)blockIdx.x) prof_stamp(prof, 8); prof_stamp(prof, 9); }
       const int m = m0 + q * 32 + lane;
       const bool row_ok = m < g.M;
       const long long d_off = (long long)b1 * g.dbs1 + (long long)b2 * g.dbs2 + (long long)m * g.ldd;
@@ -369,16 +382,21 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             ptx::bulk_commit();
           }
         }
-      } else if (g.tma_store) {
+      } else if (FAST || g.tma_store) {
         // ---- coalesced path: registers -> 128B-swizzled smem slab (32 rows x 64 cols) -> TMA store ------------------
 #pragma unroll 1
-        for (int slab = 0; slab < ((g.dbg & 4) ? 0 : BN / 64); ++slab) {
+        for (int slab = 0; slab < ((dbg & 4) ? 0 : BN / 64); ++slab) {
           const int ns = n0 + slab * 64;
           if (ns >= g.N) break;
           uint32_t dbuf, abuf = 0;
+          // epilogue trace (tools/gemm_harness trace): first tile of CTA 0, first epilogue warp, slabs 0..1
+          const bool etr = prof && blockIdx.x == 0 && t == 0 && warp == kEpiWarp0 && lane == 0 && slab < 2;
+          long long* et = etr ? prof + 148 * 16 + 128 + slab * 8 : nullptr;
+          if (etr) et[0] = clock64();
           if (gelu_save || aux_in) { dbuf = my_stage0; abuf = my_stage0 + kStageBufBytes; if (lane == 0) ptx::bulk_wait_read<0>(); }
           else { dbuf = my_stage0 + sbuf_toggle * kStageBufBytes; sbuf_toggle ^= 1u; if (lane == 0) ptx::bulk_wait_read<1>(); }
           __syncwarp();
+          if (etr) et[1] = clock64();
           if (aux_in) {
             // residual / pre-activation tile (32 rows x 64 cols) by TMA into the second staging buffer: coalesced 128-byte
             // rows instead of one 16-byte global load per thread per row
@@ -393,6 +411,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
           for (int half = 0; half < 2; ++half) {
             uint32_t raw[32];
             ld_acc(slab * 64 + half * 32, raw);
+            if (etr) et[2 + half * 2] = clock64();
             const int nb = ns + half * 32;
             float v[32];
 #pragma unroll
@@ -413,7 +432,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 float af[8]; unpack8(pk, af);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j8 * 8 + j] = gelu_tanh(af[j]);
-              } else if (g.epi != EPI_NONE) {
+              } else if (epi != EPI_NONE) {
                 float af[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) af[j] = 0.f;
@@ -421,27 +440,30 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 else if (row_ok && col_ok) unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(g.aux) + (long long)m * g.ld_aux + nc), af);
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                  v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
+                  v[j8 * 8 + j] = epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
               }
               ptx::st_shared_16(dbuf + chunk, pack8(&v[j8 * 8]));
             }
+            if (etr) et[3 + half * 2] = clock64();
           }
           ptx::fence_proxy_async();     // generic-proxy smem writes -> visible to the TMA (async proxy)
           __syncwarp();
-          if (lane == 0 && m0 + q * 32 < g.M && !(g.dbg & 1)) {
+          if (etr) et[6] = clock64();
+          if (lane == 0 && m0 + q * 32 < g.M && !(dbg & 1)) {
             ptx::tma_store_4d(&tma_d, dbuf, ns, m0 + q * 32, b2, b1);
             if (gelu_save) ptx::tma_store_4d(&tma_aux, abuf, ns, m0 + q * 32, 0, 0);
             ptx::bulk_commit();
           }
+          if (etr) et[7] = clock64();
         }
-      } else {
+      } else if constexpr (!FAST) {
         // ---- direct path (fp32 output, accumulate, or unaligned): per-thread row segments --------------------------
 #pragma unroll 1
-        for (int c = 0; c < ((g.dbg & 4) ? 0 : BN / 32); ++c) {
+        for (int c = 0; c < ((dbg & 4) ? 0 : BN / 32); ++c) {
           uint32_t raw[32];
           ld_acc(c * 32, raw);
           const int nb = n0 + c * 32;
-          if (row_ok && nb < g.N && !(g.dbg & 1)) {
+          if (row_ok && nb < g.N && !(dbg & 1)) {
             float v[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * g.alpha;
@@ -454,12 +476,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                   for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += bf[j];
                 }
               }
-              if (g.epi != EPI_NONE) {
+              if (epi != EPI_NONE) {
                 const long long a_off = (long long)m * g.ld_aux + nb;
 #pragma unroll
                 for (int j8 = 0; j8 < 4; ++j8) {
                   float af[8];
-                  if (g.epi == EPI_GELU_SAVE) {
+                  if (epi == EPI_GELU_SAVE) {
                     if (g.io_f32) {
                       float4* ap = reinterpret_cast<float4*>(reinterpret_cast<float*>(g.aux) + a_off + j8 * 8);
                       ap[0] = make_float4(v[j8 * 8], v[j8 * 8 + 1], v[j8 * 8 + 2], v[j8 * 8 + 3]);
@@ -477,7 +499,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                     ld8_any(g.aux, a_off + j8 * 8, g.io_f32, af);
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                      v[j8 * 8 + j] = g.epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
+                      v[j8 * 8 + j] = epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
                   }
                 }
               }
@@ -510,7 +532,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                   float x = v[j];
                   if (g.bias) x += ld1_any(g.bias, n, g.io_f32);
                   const long long ai = (long long)m * g.ld_aux + n;
-                  if (g.epi == EPI_GELU_SAVE) {
+                  if (epi == EPI_GELU_SAVE) {
                     if (g.io_f32) {
                       reinterpret_cast<float*>(g.aux)[ai] = x;
                     } else {
@@ -519,9 +541,9 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                       x = __bfloat162float(pre);
                     }
                     x = gelu_tanh(x);
-                  } else if (g.epi == EPI_GELU_BWD) {
+                  } else if (epi == EPI_GELU_BWD) {
                     x *= gelu_tanh_grad(ld1_any(g.aux, ai, g.io_f32));
-                  } else if (g.epi == EPI_RESIDUAL) {
+                  } else if (epi == EPI_RESIDUAL) {
                     x += ld1_any(g.aux, ai, g.io_f32);
                   }
                   if (g.d_f32) {
@@ -541,7 +563,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(tempty_bar(as));
-      if (g.prof && warp == kEpiWarp0 && lane == 0) prof_stamp(g, 10);
+      if (prof && warp == kEpiWarp0 && lane == 0) prof_stamp(prof, 10);
     }
     if (lane == 0) {
       if constexpr (RED) {
@@ -553,13 +575,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         ptx::bulk_wait_read<0>();     // staging smem must outlive the last TMA store's reads
       }
     }
-    if (g.prof && warp == kEpiWarp0 && lane == 0) prof_stamp(g, 11);
+    if (prof && warp == kEpiWarp0 && lane == 0) prof_stamp(prof, 11);
     __syncwarp();
   }
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (g.prof && threadIdx.x == 0) { prof_stamp(g, 13); g.prof[(long long)blockIdx.x * 16 + 14] = globaltimer_ns(); }
+  if (prof && threadIdx.x == 0) { prof_stamp(prof, 13); prof[(long long)blockIdx.x * 16 + 14] = globaltimer_ns(); }
   if (g.cm > 1) ptx::cluster_sync();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     ptx::tc_fence_after();
@@ -675,22 +697,22 @@ static int max_clusters(int cm) {
   at[0].val.clusterDim.x = cm; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false, false, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false, false, false, -1, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
   cache[cm] = n;
   return n;
 }
 
-template <int BN, bool F32, bool RED = false, bool DUAL = false>
+template <int BN, bool F32, bool RED = false, bool DUAL = false, int EPI = -1, bool FAST = false>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                    const GemmDev& g, int tiles, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_kernel<BN, F32, RED, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+    cudaFuncSetAttribute(gemm_kernel<BN, F32, RED, DUAL, EPI, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
     attr_done = true;
   }
   if (g.cm == 1) {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    launch_k(gemm_kernel<BN, F32, RED, DUAL>, dim3(grid), dim3(DUAL ? kThreadsDual : kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
+    launch_k(gemm_kernel<BN, F32, RED, DUAL, EPI, FAST>, dim3(grid), dim3(DUAL ? kThreadsDual : kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
     return;
   }
   // cluster launch: cm consecutive CTAs = cm consecutive M tiles of one N tile; grid is a whole number of clusters
@@ -708,7 +730,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32, RED, DUAL>, ta, tb, td, tx, g);
+  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32, RED, DUAL, EPI, FAST>, ta, tb, td, tx, g);
 }
 
 // cluster size along M: B-tile multicast divides L2->SM (or NVLink, for a ZeRO-3 peer weight) operand traffic by cm
@@ -781,26 +803,31 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
     }
     g.tma_store = ok ? 1 : 0;
   }
-  // two half-K pipelines per CTA whenever the MMA is narrow enough to be issue-bound (BN <= 128, bf16); TDS_GEMM_DUAL=0 /
-  // gemm_set_variant(1) keeps the single pipeline for A/B measurements
-  static const int dual_env = getenv("TDS_GEMM_DUAL") ? atoi(getenv("TDS_GEMM_DUAL")) : 1;
-  const bool dual = dual_env && g_variant != 1 && !f32 && bn <= 128;
+  // two half-K pipelines per CTA whenever the MMA is narrow enough to be issue-bound (BN <= 128, bf16)
+  const int T = (int)tiles;
+#define TDS_L(BN_, F32_, RED_, DUAL_, EPI_, FAST_) launch<BN_, F32_, RED_, DUAL_, EPI_, FAST_>(ta, tb, td, tx, g, T, stream)
+#define TDS_BY_BN(F32_, RED_, EPI_, FAST_)                                           \
+  do {                                                                               \
+    if (cfg == 0) TDS_L(64, F32_, RED_, !(F32_), EPI_, FAST_);                       \
+    else if (cfg == 1) TDS_L(128, F32_, RED_, !(F32_), EPI_, FAST_);                 \
+    else if (cfg == 2) TDS_L(256, F32_, RED_, false, EPI_, FAST_);                   \
+    else TDS_L(192, F32_, RED_, false, EPI_, FAST_);                                 \
+  } while (0)
   if (p.reduce_out) {
-    if (cfg == 0) { if (dual) launch<64, false, true, true>(ta, tb, td, tx, g, (int)tiles, stream); else launch<64, false, true>(ta, tb, td, tx, g, (int)tiles, stream); }
-    else if (cfg == 1) { if (dual) launch<128, false, true, true>(ta, tb, td, tx, g, (int)tiles, stream); else launch<128, false, true>(ta, tb, td, tx, g, (int)tiles, stream); }
-    else if (cfg == 2) launch<256, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
-    else launch<192, false, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    TDS_BY_BN(false, true, -1, false);
   } else if (f32) {
-    if (cfg == 0) launch<64, true>(ta, tb, td, tx, g, (int)tiles, stream);
-    else if (cfg == 1) launch<128, true>(ta, tb, td, tx, g, (int)tiles, stream);
-    else if (cfg == 2) launch<256, true>(ta, tb, td, tx, g, (int)tiles, stream);
-    else launch<192, true>(ta, tb, td, tx, g, (int)tiles, stream);
+    TDS_BY_BN(true, false, -1, false);
+  } else if (g.tma_store) {
+    // the bf16 training step lives here: epilogue functor and store path fixed at compile time
+    if (g.epi == EPI_NONE) TDS_BY_BN(false, false, EPI_NONE, true);
+    else if (g.epi == EPI_GELU_SAVE) TDS_BY_BN(false, false, EPI_GELU_SAVE, true);
+    else if (g.epi == EPI_GELU_BWD) TDS_BY_BN(false, false, EPI_GELU_BWD, true);
+    else TDS_BY_BN(false, false, EPI_RESIDUAL, true);
   } else {
-    if (cfg == 0) { if (dual) launch<64, false, false, true>(ta, tb, td, tx, g, (int)tiles, stream); else launch<64, false>(ta, tb, td, tx, g, (int)tiles, stream); }
-    else if (cfg == 1) { if (dual) launch<128, false, false, true>(ta, tb, td, tx, g, (int)tiles, stream); else launch<128, false>(ta, tb, td, tx, g, (int)tiles, stream); }
-    else if (cfg == 2) launch<256, false>(ta, tb, td, tx, g, (int)tiles, stream);
-    else launch<192, false>(ta, tb, td, tx, g, (int)tiles, stream);
+    TDS_BY_BN(false, false, -1, false);
   }
+#undef TDS_BY_BN
+#undef TDS_L
 }
 
 }  // namespace tds

@@ -102,6 +102,28 @@ static float time_warm(const tds::GemmParams& p, int pair, int iters = 30) {
   CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
   return ms * 1e3f / iters;
 }
+// the same 30 launches as ONE CUDA graph (how the training step actually runs them): per-launch time inside the graph
+static float time_graph(const tds::GemmParams& p, int pair, int iters = 30) {
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  tds::GemmParams q = p;
+  cudaGraph_t graph; cudaGraphExec_t exec;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
+  for (int i = 0; i < iters; ++i) { if (!(pair && tds::gemm2_bf16(q, st))) tds::gemm_bf16(q, st); }
+  CK(cudaStreamEndCapture(st, &graph));
+  CK(cudaGraphInstantiate(&exec, graph, 0));
+  for (int i = 0; i < 3; ++i) CK(cudaGraphLaunch(exec, st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < 5; ++i) CK(cudaGraphLaunch(exec, st));
+  CK(cudaEventRecord(e1, st));
+  CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
+  CK(cudaGraphExecDestroy(exec)); CK(cudaGraphDestroy(graph)); CK(cudaStreamDestroy(st));
+  return ms * 1e3f / (5 * iters);
+}
 static float time_cold(const tds::GemmParams& p, int pair, int iters = 9) {
   std::vector<float> v;
   cudaEvent_t e0, e1;
@@ -172,7 +194,7 @@ int main(int argc, char** argv) {
         printf(" %5.1f", time_warm(p, 0));
       }
       tds::GemmParams p = make_params(s, bf, -1, !nobias);
-      printf(" (%5.1f)", time_cold(p, 0));
+      printf(" (%5.1f) graph %5.2f", time_cold(p, 0), time_graph(p, 0));
     }
     {
       tds::gemm_set_variant(0);
@@ -217,6 +239,20 @@ int main(int argc, char** argv) {
         printf("\n      kb%d:", kb + 6);
         for (int i = 1; i <= 3; ++i) printf(" %5lld", tr[i] - tr[0]);
         if (kb < 3) printf(" | %5lld", h[148 * 16 + 64 + (kb + 1) * 8] - tr[0]);
+      }
+      printf("\n    epilogue trace per 64-col slab (cycles: wait_read+sync, ld0, st0, ld1, st1, fence+sync, tma_store):");
+      for (int sl = 0; sl < 2; ++sl) {
+        const long long* tr = &h[148 * 16 + 128 + sl * 8];
+        if (!tr[0]) continue;
+        printf("\n      slab%d:", sl);
+        for (int i = 1; i <= 7; ++i) printf(" %5lld", tr[i] - tr[0]);
+      }
+      // phase medians over CTAs in ns-equivalent cycles of each warp's own clock
+      {
+        std::vector<long long> epi, tot;
+        for (int b = 0; b < 148; ++b) if (h[b * 16 + 1]) { epi.push_back(h[b * 16 + 10] - h[b * 16 + 9]); tot.push_back(h[b * 16 + 14] - h[b * 16 + 0]); }
+        std::sort(epi.begin(), epi.end()); std::sort(tot.begin(), tot.end());
+        printf("\n    median over CTAs: epilogue body %lld cycles, CTA lifetime %lld ns", epi[epi.size() / 2], tot[tot.size() / 2]);
       }
     }
     printf("\n");
