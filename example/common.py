@@ -65,22 +65,16 @@ def torch_dtype(args):
 
 
 def train_loop(model, optimizer, x, y, args, rank=0, distributed=False):
-    step = None
-    if args.graph:
-        from tiny_deepspeed_b200 import TrainStep
-        step = TrainStep(model, optimizer)
+    """``--graph`` replays the whole step as one CUDA graph; either way the step goes through TrainStep, which also carries the
+    optional watchdog (TDS_WATCHDOG_S) and JSON-lines metrics (TDS_METRICS / TDS_METRICS_EVERY)."""
+    from tiny_deepspeed_b200 import TrainStep
+    step = TrainStep(model, optimizer, use_graph=bool(args.graph))
     for i in range(args.iters):
-        if step is not None:
-            loss = step(x, y)
-        else:
-            if hasattr(model, "require_backward_grad_sync"):
-                model.require_backward_grad_sync = True  # one-shot flag, re-armed every iteration
-            _, loss = model(x, y)
-            loss.backward()
-            optimizer.step()
+        loss = step(x, y)                  # eager: model.require_backward_grad_sync re-armed, fwd, bwd, optimizer.step()
         loss = loss.detach().clone()
         if distributed:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM)
             loss /= dist.get_world_size()
         if rank == 0:
             print(format_loss_line(i, loss.item()), flush=True)
+    step.finish()

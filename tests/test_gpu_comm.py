@@ -321,3 +321,134 @@ def test_fused_reduce_scatter_matches_dist_backend(mode):
         assert rel < 2e-2, (mode, n, float(rel))
         for r in range(1, world):
             assert torch.equal(nat[r][1][n], a), (mode, n, r)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: bucketed ZeRO step inside backward, gradient ring (real ZeRO-2/3 gradient sharding), ADVICE r1 regressions
+# ---------------------------------------------------------------------------------------------------------------------
+def _zero3_from_real_model(rank, world, backend):
+    """The reference's own usage: ZeroN(GPT2Model(cfg).to(rank), parts) with an already materialised model (ADVICE r1 high:
+    the native ZeRO-3 policy used to empty non-owned tensors BEFORE the initial broadcast and desynchronise NCCL)."""
+    import torch.distributed as dist
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    dev = torch.device("cuda", rank)
+    cfg = gpt2_config("tiny", n_layer=2, n_embd=256, n_head=4, vocab_size=2048, block_size=128)
+    with torch.device("meta"):
+        parts, _ = tds.partition_tensors(OrderedDict(GPT2Model(cfg).named_parameters()), num_parts=world)
+    torch.manual_seed(11 + rank)                       # replicas DIFFER before wrapping: the wrapper must fix that
+    model = GPT2Model(cfg).to(device=dev, dtype=torch.bfloat16)
+    model = tds.Zero3(model, parts, backend=backend)
+    opt = tds.Zero3AdamW(model.module.named_parameters(), lr=1e-3, weight_decay=0.1, param_part_table=parts,
+                         ranks_map=[f"cuda:{i}" for i in range(world)])
+    g = torch.Generator().manual_seed(5)
+    x = torch.randint(0, cfg.vocab_size, (2, 128), generator=g).to(dev)
+    losses = []
+    for _ in range(4):
+        model.require_backward_grad_sync = True
+        _, loss = model(x, x)
+        loss.backward()
+        opt.step()
+        l = loss.detach().float().clone()
+        dist.all_reduce(l)
+        losses.append(float(l) / world)
+    return losses, model.backend
+
+
+def test_zero3_native_accepts_materialised_model():
+    world = _world()
+    nat = run_gpu_distributed(_zero3_from_real_model, world=world, args=("native",), timeout=300)
+    ref = run_gpu_distributed(_zero3_from_real_model, world=world, args=("dist",), timeout=300)
+    assert nat[0][1] == "native"
+    assert nat[0][0][-1] < nat[0][0][0]
+    assert nat[0][0] == pytest.approx(ref[0][0], rel=2e-2, abs=2e-2), (nat[0][0], ref[0][0])
+
+
+def _peak_memory(rank, world, mode):
+    """Peak HBM of one rank (torch allocator + symmetric buffers) for a model whose gradients dominate the activations."""
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    from tiny_deepspeed_b200.parallel import materialize_
+    dev = torch.device("cuda", rank)
+    cfg = gpt2_config("tiny", n_layer=8, n_embd=1024, n_head=8, vocab_size=8192, block_size=128)
+    with torch.device("meta"):
+        parts, _ = tds.partition_tensors(OrderedDict(GPT2Model(cfg).named_parameters()), num_parts=world, strategy="balanced")
+        model = GPT2Model(cfg).to(torch.bfloat16)
+    materialize_(model, device=dev, seed=2)
+    torch.cuda.synchronize(dev)
+    torch.cuda.reset_peak_memory_stats(dev)
+    W = {"zero1": tds.Zero1, "zero2": tds.Zero2}[mode]
+    O = {"zero1": tds.Zero1AdamW, "zero2": tds.Zero2AdamW}[mode]
+    model = W(model, parts, backend="native", bucket_bytes=8 << 20)
+    opt = O(model.module.named_parameters(), lr=1e-3, weight_decay=0.1, param_part_table=parts,
+            ranks_map=[f"cuda:{i}" for i in range(world)])
+    x = torch.randint(0, cfg.vocab_size, (1, 128), device=dev)
+    for _ in range(3):
+        model.require_backward_grad_sync = True
+        _, loss = model(x, x)
+        loss.backward()
+        opt.step()
+    torch.cuda.synchronize(dev)
+    psi = sum(int(torch.Size(p._tds_shape).numel()) for p in model.module.parameters())
+    return dict(peak=torch.cuda.max_memory_allocated(dev) + model.policy.symmetric_bytes(), psi=psi,
+                grad_buffer_bytes=int(model.policy.G.local.numel()), ring=bool(model.policy.ring), loss=float(loss))
+
+
+def test_zero2_shards_gradients_peak_memory():
+    """SURVEY §4-3(c) / VERDICT r1: ZeRO-2 must hold less than ZeRO-1 — non-owners keep at most a ring of gradient buckets."""
+    world = _world()
+    z1 = run_gpu_distributed(_peak_memory, world=world, args=("zero1",), timeout=300)
+    z2 = run_gpu_distributed(_peak_memory, world=world, args=("zero2",), timeout=300)
+    psi = z1[0]["psi"]
+    assert z2[0]["ring"] and not z1[0]["ring"]
+    assert z1[0]["grad_buffer_bytes"] >= 2 * psi                         # ZeRO-1: full bf16 gradient buffer
+    assert z2[0]["grad_buffer_bytes"] <= 0.5 * z1[0]["grad_buffer_bytes"]    # ZeRO-2: 3 x 8 MB slots (+ largest tensor)
+    for r in range(world):
+        assert z2[r]["peak"] < z1[r]["peak"] - 0.4 * 2 * psi, (r, z1[r], z2[r])
+        # 2 Psi params + 2 Psi ring at most + (4+4+4) Psi / N optimizer state + slack for activations / staging
+        assert z2[r]["peak"] < 2 * psi + z2[r]["grad_buffer_bytes"] + 12 * psi / world + 2 * psi / world + (96 << 20), z2[r]
+    assert abs(z1[0]["loss"] - z2[0]["loss"]) < 0.05
+
+
+def _native_checkpoint(rank, world, tmp):
+    """(1) load_state_dict before the first fused step, (2) the step counter survives graph replays."""
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    from tiny_deepspeed_b200.parallel import materialize_
+    from tiny_deepspeed_b200.utils import save_checkpoint, load_checkpoint
+    dev = torch.device("cuda", rank)
+    cfg = gpt2_config("tiny", n_layer=2, n_embd=256, n_head=4, vocab_size=2048, block_size=128)
+
+    def build(seed):
+        with torch.device("meta"):
+            parts, _ = tds.partition_tensors(OrderedDict(GPT2Model(cfg).named_parameters()), num_parts=world)
+            m = GPT2Model(cfg).to(torch.bfloat16)
+        materialize_(m, device=dev, seed=seed)
+        m = tds.Zero1(m, parts, backend="native")
+        o = tds.Zero1AdamW(m.module.named_parameters(), lr=1e-3, weight_decay=0.1, param_part_table=parts,
+                           ranks_map=[f"cuda:{i}" for i in range(world)])
+        return parts, m, o
+
+    x = torch.randint(0, cfg.vocab_size, (2, 128), device=dev, generator=torch.Generator(device=dev).manual_seed(3))
+    parts, m1, o1 = build(1)
+    step = tds.TrainStep(m1, o1, use_graph=True, warmup=2)
+    for _ in range(6):
+        step(x, x)
+    torch.cuda.synchronize()
+    sd = o1.state_dict()
+    save_checkpoint(tmp, m1, o1, table=parts, step=6)
+    l_next = float(step(x, x))                                         # step 7 of the original run
+    parts2, m2, o2 = build(9)                                          # different init: everything must come from the files
+    load_checkpoint(tmp, m2, o2)                                       # BEFORE any fused step of o2
+    step2 = tds.TrainStep(m2, o2, use_graph=False)
+    l_resumed = float(step2(x, x))
+    return dict(step=sd["step"], n_state=len(sd["state"]), has_moments=all("exp_avg" in v for v in sd["state"].values()),
+                l_next=l_next, l_resumed=l_resumed, resumed_step=o2.step_count)
+
+
+def test_native_zero_checkpoint_roundtrip(tmp_path):
+    res = run_gpu_distributed(_native_checkpoint, world=2, args=(str(tmp_path),), timeout=300)
+    for r in res:
+        assert r["step"] == 6 and r["n_state"] > 0 and r["has_moments"], r
+        assert r["resumed_step"] == 7, r
+        assert r["l_resumed"] == pytest.approx(r["l_next"], rel=2e-3, abs=2e-3), r

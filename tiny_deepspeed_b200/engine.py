@@ -24,7 +24,8 @@ __all__ = ["TrainStep"]
 
 class TrainStep:
     def __init__(self, model, optimizer, *, use_graph: Optional[bool] = None, warmup: int = 3,
-                 grad_sync: bool = True, overlap_step: Optional[bool] = None):
+                 grad_sync: bool = True, overlap_step: Optional[bool] = None, watchdog_s: Optional[float] = None,
+                 metrics_path: Optional[str] = None, metrics_every: Optional[int] = None):
         self.model = model
         self.optimizer = optimizer
         self.grad_sync = grad_sync
@@ -46,6 +47,17 @@ class TrainStep:
             # measured on B200 (profiles/r1_overlap_pdl.md): 4.87 ms without vs 4.93 ms with -> opt-in
             overlap_step = os.environ.get("TDS_OVERLAP_STEP", "0") != "0"
         self.overlap = self._setup_overlap() if (overlap_step and self.device.type == "cuda") else None
+        # ---- aux subsystems: failure detection + metrics, both off unless asked for -------------------------
+        import os
+        from .utils import MetricsLogger, Watchdog
+        if watchdog_s is None and os.environ.get("TDS_WATCHDOG_S"):
+            watchdog_s = float(os.environ["TDS_WATCHDOG_S"])
+        self.watchdog = Watchdog(timeout_s=watchdog_s, name="train step") if watchdog_s else None
+        self._inflight = None                       # CUDA event behind the previous step (watchdog mode only)
+        metrics_path = metrics_path or os.environ.get("TDS_METRICS")
+        self.metrics = MetricsLogger(metrics_path) if metrics_path else None
+        self.metrics_every = int(metrics_every or os.environ.get("TDS_METRICS_EVERY", "50"))
+        self._win_event, self._win_step, self._tokens_per_step = None, 0, 0
 
     def _setup_overlap(self):
         """Optimizer-in-backward (optim/overlap.py) where the gradient is final inside backward: single process
@@ -112,7 +124,81 @@ class TrainStep:
                 "Drop those tensors first, or construct TrainStep(..., use_graph=False).") from e
         # capture only records: the captured step has not executed yet
 
+    # ------------------------------------------------------------------ aux: watchdog / metrics
+    def _policy(self):
+        return getattr(self.model, "policy", None)
+
+    def _guard_begin(self):
+        """Watchdog mode keeps at most one step in flight: wait for the previous one (bounded by the watchdog armed when
+        it was launched), surface device-side collective timeouts, then arm for the step about to be queued."""
+        if self.watchdog is None:
+            return
+        if self._inflight is not None:
+            self._inflight.synchronize()
+            self.watchdog.disarm()
+            from .utils import check_device_flags
+            check_device_flags(self._policy())
+        self.watchdog.arm()
+
+    def _guard_end(self):
+        if self.watchdog is not None and self.device.type == "cuda":
+            self._inflight = torch.cuda.Event()
+            self._inflight.record(torch.cuda.current_stream(self.device))
+        elif self.watchdog is not None:
+            self.watchdog.disarm()
+
+    def finish(self):
+        """Drain the last step (watchdog bookkeeping) — call once after the training loop."""
+        if self.watchdog is not None:
+            if self._inflight is not None:
+                self._inflight.synchronize()
+                self._inflight = None
+            self.watchdog.disarm()
+            from .utils import check_device_flags
+            check_device_flags(self._policy())
+
+    def _log_metrics(self, loss, ntokens):
+        """Every ``metrics_every`` steps: device-timed ms/step and tokens/s of the window, loss, peak HBM (+ symmetric
+        buffers), launches per step, communication counters of the policy.  One host sync per window."""
+        if self.metrics is None:
+            return
+        self._tokens_per_step = ntokens
+        if self.device.type != "cuda":
+            if self.steps % self.metrics_every == 0:
+                self.metrics.log(step=self.steps, loss=float(loss))
+            return
+        if self._win_event is None:
+            self._win_event = torch.cuda.Event(enable_timing=True)
+            self._win_event.record()
+            self._win_step = self.steps
+            return
+        if self.steps - self._win_step < self.metrics_every:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        ev.synchronize()
+        ms = self._win_event.elapsed_time(ev) / (self.steps - self._win_step)
+        pol = self._policy()
+        world = getattr(pol, "world", 1) if pol is not None else 1
+        symm_b = pol.symmetric_bytes() if hasattr(pol, "symmetric_bytes") else 0
+        rec = dict(step=self.steps, loss=float(loss), ms_per_step=round(ms, 4),
+                   tokens_per_s=round(ntokens * world / (ms * 1e-3), 1), world=world,
+                   peak_hbm_bytes=int(torch.cuda.max_memory_allocated(self.device) + symm_b),
+                   launches_per_step=self.launches_per_step)
+        if pol is not None and hasattr(pol, "stats"):
+            rec["comm"] = dict(pol.stats)
+        self.metrics.log(**rec)
+        self._win_event, self._win_step = ev, self.steps
+
     def __call__(self, idx, targets):
+        self._guard_begin()
+        loss = self._call(idx, targets)
+        self._guard_end()
+        if self.metrics is not None:
+            self._log_metrics(loss, int(idx.numel()))
+        return loss
+
+    def _call(self, idx, targets):
         self.steps += 1
         if not self.use_graph:
             if idx.device != self.device:

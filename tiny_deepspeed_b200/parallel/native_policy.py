@@ -9,9 +9,15 @@ views over those buffers.
   ``multimem.st``) runs on the communication stream while backward continues.  The last bucket (the
   embedding gradients, produced by the final backward kernel) is hidden under the Adam update of everything
   that was reduced earlier (``flush_async`` / ``join``).
-* **ZeRO-1/2** — one fused kernel per step on the owner: switch-reduced gradient → scale → Adam on
-  the local fp32 master/moments → bf16 parameter multicast to all ranks
-  (``csrc/comm_sm100.cu: zero_fused_adam_kernel``).  Non-owners never materialise ``param.grad``.
+* **ZeRO-1/2** — the reference's move (collective right after each gradient, `zero1/module.py:17-24`) at bucket
+  granularity: as soon as a bucket of gradients is complete, ONE fused kernel on the communication stream —
+  switch-reduced gradient → scale → Adam on the owner's fp32 master/moments → bf16 parameter multicast to all ranks
+  (``csrc/comm_sm100.cu: zero_fused_adam_kernel``) — runs underneath the rest of backward.  ZeRO-1 keeps the
+  full-size gradient buffer; ZeRO-2/3 write gradients into a small symmetric *ring* of bucket-sized slots that is
+  recycled as backward proceeds (slot b is reused by bucket b + nslots once every rank's step kernel for bucket b has
+  finished), so a non-owner holds at most `nslots` buckets of gradients (`zero2/module.py:26-36` drops them one by one).
+  Optimizers the fused kernel does not cover (SGD, amsgrad, fp32 parameters) take the same bucket pipeline with a
+  reduce-to-owner kernel per owner run + a copy into the owner's persistent shard, and update at ``step()``.
 * **ZeRO-3** — a tensor is resident on its owner only (the symmetric parameter buffer is sized for the
   largest owner share, not for the model).  ``fetch="push"`` (default): the owner ``multimem.st``-pushes a
   group of consecutively used tensors (≈ one layer, ≤ 16 MB) into a 4-slot symmetric staging ring on every
@@ -49,7 +55,8 @@ class NativePolicy(CommPolicy):
     rs_names = frozenset()
 
     def __init__(self, mode: str, model: torch.nn.Module, *, table: Optional[Dict[str, int]] = None, group=None,
-                 average: bool = False, bucket_bytes: int = 64 << 20, comm_blocks: int = 32):
+                 average: bool = False, bucket_bytes: int = 64 << 20, comm_blocks: int = 32,
+                 grad_accumulation: bool = False, ring_slots: int = 3):
         self.mode = mode
         self.name = f"native-{mode}"
         self.group = group
@@ -75,6 +82,7 @@ class NativePolicy(CommPolicy):
         self.f32 = self.dtype == torch.float32
         self.esize = 4 if self.f32 else 2
         self.table = table or {n: 0 for n, _ in named}
+        import os
         self.comm = symm.Comm(self.device, group)
         self.comm_stream = torch.cuda.Stream(self.device)
 
@@ -83,11 +91,46 @@ class NativePolicy(CommPolicy):
         self.params: "OrderedDict[str, torch.nn.Parameter]" = OrderedDict(named)
         self.shape = {n: tuple(getattr(p, "_tds_shape", p.shape)) for n, p in named}
         self.numel = {n: int(torch.Size(self.shape[n]).numel()) for n in self.names}
-        self.goff, off = {}, 0                       # gradient buffer: every tensor, registration order
+        # ---- bucketing: backward produces tensors roughly in reverse registration order ---------------------------------
+        self.buckets: List[List[str]] = []
+        cur, cur_bytes = [], 0
+        for n in reversed(self.names):
+            cur.append(n)
+            cur_bytes += _pad(self.numel[n]) * self.esize
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {n: i for i, b in enumerate(self.buckets) for n in b}
+        # ---- gradient buffer layout ------------------------------------------------------------------------------------
+        # full: every tensor, registration order (DDP, ZeRO-1, or gradient accumulation requested)
+        # ring: ZeRO-2/3 — `nslots` bucket-sized slots recycled during backward (real gradient sharding: a rank never
+        #       holds more than nslots buckets of full gradients + its own reduced shard)
+        self.grad_accumulation = bool(grad_accumulation)
+        # TDS_ZERO_OVERLAP=0: classic schedule (every bucket's step kernel after the last backward kernel) — needs the
+        # full-size buffer, so it also switches the ring off
+        self._zero_overlap = os.environ.get("TDS_ZERO_OVERLAP", "1") != "0"
+        self.ring = mode in ("zero2", "zero3") and self.world > 1 and not self.grad_accumulation and \
+            self._zero_overlap and os.environ.get("TDS_ZERO_RING", "1") != "0"
+        self.foff, off = {}, 0                       # full layout: every tensor, registration order
         for n in self.names:
-            self.goff[n] = off
+            self.foff[n] = off
             off += _pad(self.numel[n])
-        self.gtotal = off
+        self.ftotal = off
+        self.goff = {}
+        if self.ring:
+            self.nslots_g = max(1, min(int(os.environ.get("TDS_RING_SLOTS", ring_slots)), len(self.buckets)))
+            self.slot_elems = max(sum(_pad(self.numel[n]) for n in b) for b in self.buckets)
+            for bi, b in enumerate(self.buckets):
+                off = (bi % self.nslots_g) * self.slot_elems
+                for n in b:
+                    self.goff[n] = off
+                    off += _pad(self.numel[n])
+            self.gtotal = self.nslots_g * self.slot_elems
+        else:
+            self.goff = dict(self.foff)
+            self.gtotal = self.ftotal
         self.poff = {}                               # parameter buffer
         if mode == "zero3":
             share = [0] * self.world                 # owner-only layout: offsets inside the owner's region
@@ -97,8 +140,8 @@ class NativePolicy(CommPolicy):
                 share[r] += _pad(self.numel[n])
             self.ptotal = max(max(share), ALIGN)
         else:
-            self.poff = dict(self.goff)
-            self.ptotal = self.gtotal
+            self.poff = dict(self.foff)
+            self.ptotal = self.ftotal
         self.G = symm.alloc(self.gtotal * self.esize, self.device, group)
         self.P = symm.alloc(self.ptotal * self.esize, self.device, group)
         self.gflat = self.G.local.view(self.dtype)
@@ -121,18 +164,6 @@ class NativePolicy(CommPolicy):
         torch.cuda.synchronize(self.device)
         self.comm.barrier()
 
-        # ---- bucketing (DDP): backward produces tensors roughly in reverse registration order -----------
-        self.buckets: List[List[str]] = []
-        cur, cur_bytes = [], 0
-        for n in reversed(self.names):
-            cur.append(n)
-            cur_bytes += _pad(self.numel[n]) * self.esize
-            if cur_bytes >= bucket_bytes:
-                self.buckets.append(cur)
-                cur, cur_bytes = [], 0
-        if cur:
-            self.buckets.append(cur)
-        self.bucket_of = {n: i for i, b in enumerate(self.buckets) for n in b}
         # ---- ZeRO-3 parameter fetch ----------------------------------------------------------------------------
         import os
         self.fetch = os.environ.get("TDS_ZERO3_FETCH", "push")     # "push": owner multicast + prefetch; "peer": GEMM pulls
@@ -194,6 +225,12 @@ class NativePolicy(CommPolicy):
 
     # ------------------------------------------------------------------------------------------ helpers
     overlap = None   # optim.overlap.StepOverlap bound to the comm stream (engine.TrainStep sets it for DDP)
+    _opt = None      # sharded optimizer bound by its constructor (bind_optimizer): lets ZeRO buckets step inside backward
+
+    def bind_optimizer(self, opt):
+        """Called by the sharded optimizers' constructors: with the optimizer known, a completed ZeRO bucket can run its
+        reduce -> Adam -> multicast kernel while backward is still producing the next one."""
+        self._opt = opt
 
     def _reset_round(self):
         self._await_update = []
@@ -201,16 +238,38 @@ class NativePolicy(CommPolicy):
         self._ready = [0] * len(self.buckets)
         self._launched = [False] * len(self.buckets)
         self._synced_any = False
+        self._step_opened = False
+        self._zero_deferred = []          # complete ZeRO buckets waiting for one more grad_ready (their dX GEMMs)
+        self._slot_waited = [False] * len(self.buckets)
+        self._generic_round = False       # a bucket of this round went through the generic reduce-to-owner path
 
     def _owner(self, name):
         return self.table[name]
 
     # ------------------------------------------------------------------------------------------ gradients
+    def _wait_slot(self, b):
+        """Ring layout: bucket b is about to be written into the slot bucket b - nslots used.  Every rank's step kernel
+        of that older bucket must have finished (its trailing flag barrier is global), then the compute stream may go on."""
+        old = b - self.nslots_g
+        if old < 0 or self._slot_waited[b]:
+            return
+        if not self._launched[old]:
+            if self._ready[old] != len(self.buckets[old]):
+                raise RuntimeError(
+                    f"native ZeRO gradient ring: bucket {b} starts before bucket {old} is complete — backward visits "
+                    f"parameters too far out of registration order for {self.nslots_g} slots (raise TDS_RING_SLOTS or pass "
+                    f"grad_accumulation=True for the full-size buffer)")
+            self._flush_zero_buckets(upto=old)
+        torch.cuda.current_stream(self.device).wait_event(self._bucket_event[old])
+        self._slot_waited[b] = True
+
     def grad_out(self, param):
         n = self._name_of[id(param)]
         if self.fused_rs and n in self.rs_names:
             # the dW GEMM adds into the owner's fp32 buffer (ops.gemm sees `_tds_reduce`); stubbed runs stay rank-local
             return (self._rs_local[n] if self.comm_stub else self._rs_view[n]), False
+        if self.ring:
+            self._wait_slot(self.bucket_of[n])
         return self.gview[n], (n in self._accumulated)
 
     def grad_ready(self, param, grad):
@@ -219,6 +278,7 @@ class NativePolicy(CommPolicy):
             if getattr(param, "bwd_sync", False):
                 param.bwd_sync = False
                 self._synced_any = True
+                self._zero_bucket_progress(n)
             return
         if grad.data_ptr() != self.gview[n].data_ptr():        # op ignored `out` (should not happen): copy in
             if n in self._accumulated:
@@ -227,13 +287,18 @@ class NativePolicy(CommPolicy):
                 self.gview[n].copy_(grad)
         self._accumulated.add(n)
         owner_like = self.mode in ("ddp", "zero1") or self._owner(n) == self.rank
-        if owner_like and param.numel() > 0:
+        if owner_like and param.numel() > 0 and not self.ring:
             param.grad = self.gview[n]
         if not getattr(param, "bwd_sync", False):
+            if self.ring:
+                raise NotImplementedError("gradient accumulation (a backward without grad sync) needs the full-size gradient "
+                                          "buffer: wrap with Zero2/Zero3(..., grad_accumulation=True)")
             return
         param.bwd_sync = False
         self._synced_any = True
-        if self.mode == "ddp" and self.world > 1:
+        if self.world == 1:
+            return
+        if self.mode == "ddp":
             b = self.bucket_of[n]
             self._ready[b] += 1
             # the all-reduce only touches the gradient buffer, so a bucket can go the moment its last dW is enqueued;
@@ -247,6 +312,105 @@ class NativePolicy(CommPolicy):
             if self._ready[b] == len(self.buckets[b]) and not self._launched[b]:
                 self._launch_bucket(b)
                 self._await_update.append(b)
+        else:
+            self._zero_bucket_progress(n)
+
+    # ---- ZeRO-1/2/3: a completed bucket goes to the communication stream while backward continues ---------------------
+    def _zero_bucket_progress(self, n):
+        b = self.bucket_of[n]
+        # buckets completed at an EARLIER grad_ready: the dX GEMMs that still read their parameters are enqueued by now,
+        # so the step kernel (which rewrites those parameters on every rank) may be ordered behind the compute stream
+        if self._zero_deferred:
+            for pb in self._zero_deferred:
+                self._launch_zero_bucket(pb)
+            self._zero_deferred = []
+        self._ready[b] += 1
+        if self._zero_overlap and self._ready[b] == len(self.buckets[b]) and not self._launched[b]:
+            self._zero_deferred.append(b)
+
+    def _flush_zero_buckets(self, upto=None):
+        """Launch every complete bucket that has not gone yet (all of them at the end of backward)."""
+        for b in list(self._zero_deferred):
+            if upto is None or b <= upto:
+                self._launch_zero_bucket(b)
+        self._zero_deferred = [b for b in self._zero_deferred if not self._launched[b]]
+        if upto is None:
+            for b, names in enumerate(self.buckets):
+                if not self._launched[b] and self._ready[b] > 0:
+                    self._launch_zero_bucket(b)
+
+    def _fusable(self, opt) -> bool:
+        from ..optim.adamw import AdamW
+        return opt is not None and isinstance(opt, AdamW) and not opt.amsgrad and not self.f32 and self.world > 1
+
+    def _launch_zero_bucket(self, b):
+        if self._launched[b]:
+            return
+        names = self.buckets[b]
+        opt = self._opt
+        fused = self._fusable(opt) and not self._generic_round
+        if not fused:
+            self._generic_round = True
+        cur = torch.cuda.current_stream(self.device)
+        if fused:
+            st = self._ensure_opt_state(opt)
+            if not self._step_opened:                  # this step's counter, once, on the compute stream before the fork
+                opt.step_count += 1
+                self._step_opened = True
+            step_dev = opt._device_step(self.device)
+        self.comm_stream.wait_stream(cur)
+        with torch.cuda.stream(self.comm_stream):
+            if fused:
+                self._fused_bucket_step(opt, st, b, step_dev)
+            else:
+                self._reduce_bucket_to_owners(b)
+            ev = torch.cuda.Event()
+            ev.record(self.comm_stream)
+        self._bucket_event[b] = ev
+        self._launch_order.append(b)
+        self._launched[b] = True
+        self.stats["bytes"] += sum(_pad(self.numel[n]) for n in names) * self.esize
+
+    def _bucket_runs(self, b):
+        """Owner runs of bucket b in gradient-buffer order: [(owner, [names...])] with contiguous gradient offsets."""
+        runs = []
+        for n in sorted(self.buckets[b], key=lambda k: self.goff[k]):
+            o = self._owner(n)
+            if runs and runs[-1][0] == o and self.goff[runs[-1][1][-1]] + _pad(self.numel[runs[-1][1][-1]]) == self.goff[n]:
+                runs[-1][1].append(n)
+            else:
+                runs.append((o, [n]))
+        return runs
+
+    def _reduce_bucket_to_owners(self, b):
+        """Generic optimizers (SGD, amsgrad, fp32 parameters): one reduce-to-owner kernel per owner run of the bucket
+        (instead of one per tensor), then — ring layout — a copy of the owner's reduced range into its persistent shard."""
+        for owner, names in self._bucket_runs(b):
+            lo = self.goff[names[0]]
+            n_el = sum(_pad(self.numel[k]) for k in names)
+            if not self.comm_stub:
+                self.comm.reduce_to(self.G, lo, n_el, owner, f32=self.f32, scale=self.scale, blocks=self.comm_blocks, channel=1)
+            if owner == self.rank:
+                for k in names:
+                    p = self.params[k]
+                    if self.ring:
+                        dst = self._own_grad(k)
+                        dst.copy_(self.gview[k])
+                        p.grad = dst
+                    elif p.numel() > 0:
+                        p.grad = self.gview[k]
+
+    def _own_grad(self, name):
+        """Ring layout: persistent home of an OWNED tensor's reduced gradient (the ring slot is recycled)."""
+        if getattr(self, "_gown", None) is None:
+            owned = [k for k in self.names if self._owner(k) == self.rank]
+            self._gown_off, off = {}, 0
+            for k in owned:
+                self._gown_off[k] = off
+                off += _pad(self.numel[k])
+            self._gown = torch.zeros(max(off, ALIGN), dtype=self.dtype, device=self.device)
+        o = self._gown_off[name]
+        return self._gown[o: o + self.numel[name]].view(self.shape[name])
 
     def _launch_complete_buckets(self, flush=False):
         for b, names in enumerate(self.buckets):
@@ -309,11 +473,10 @@ class NativePolicy(CommPolicy):
             self._join_pending = False
             self._accumulated.clear()
             self._reset_round()
-        elif self.mode != "ddp" and self._synced_any and self._opt_state is None:
-            # generic (non-fused) optimizer: reduce every tensor onto its owner with our kernel, tensor by tensor
-            for n in self.names:
-                self.comm.reduce_to(self.G, self.goff[n], _pad(self.numel[n]), self._owner(n), f32=self.f32, scale=self.scale,
-                                    blocks=self.comm_blocks, channel=0)
+        elif self.mode != "ddp" and self.world > 1 and self._synced_any and not self._step_opened:
+            # generic optimizer: every bucket is reduced onto its owners (most of them already were, during backward)
+            self._flush_zero_buckets()
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
             self._accumulated.clear()
             self._reset_round()
             self._end_round_zero3()
@@ -435,8 +598,7 @@ class NativePolicy(CommPolicy):
 
     # ------------------------------------------------------------------------------------------ fused optimizer step
     def owns_optimizer_state(self, opt) -> bool:
-        from ..optim.adamw import AdamW
-        return self.mode != "ddp" and self.world > 1 and isinstance(opt, AdamW) and not opt.amsgrad and not self.f32
+        return self.mode != "ddp" and self._fusable(opt)
 
     def _ensure_opt_state(self, opt):
         if self._opt_state is not None:
@@ -457,53 +619,50 @@ class NativePolicy(CommPolicy):
             sl = slice(soff[n], soff[n] + self.numel[n])
             opt.state[n] = {"exp_avg": m[sl].view(self.shape[n]), "exp_avg_sq": v[sl].view(self.shape[n]),
                             "master": master[sl].view(self.shape[n])}
-        ranges = [[self.goff[n], _pad(self.numel[n]), soff[n], self.poff[n]] for n in owned]
-        # every rank must launch the same number of (barrier-carrying) fused kernels: the rank owning most tensors decides
-        per_rank = [sum(1 for n in self.names if self._owner(n) == r) for r in range(self.world)]
         max_ranges = int(ops.ext().COMM_MAX_RANGES)
-        self._min_launches = max(1, max((c + max_ranges - 1) // max_ranges for c in per_rank))
-        self._opt_state = dict(master=master, m=m, v=v, ranges=ranges, owned=owned)
+        owned_set = set(owned)
+        bucket_ranges, bucket_min = [], []
+        for names in self.buckets:
+            mine = sorted((n for n in names if n in owned_set), key=lambda k: self.goff[k])
+            rs = [[self.goff[n], _pad(self.numel[n]), soff[n], self.poff[n]] +
+                  ([int(n in self.rs_names)] if self.fused_rs else []) for n in mine]
+            bucket_ranges.append(rs)
+            # every rank must launch the same number of (barrier-carrying) kernels per bucket: the rank owning most decides
+            per_rank = [sum(1 for n in names if self._owner(n) == r) for r in range(self.world)]
+            bucket_min.append(max(1, max((c + max_ranges - 1) // max_ranges for c in per_rank)))
+        self._opt_state = dict(master=master, m=m, v=v, owned=owned, bucket_ranges=bucket_ranges, bucket_min=bucket_min)
         return self._opt_state
 
-    def fused_optimizer_step(self, opt) -> bool:
-        """ZeRO-1/2/3 + Adam: reduce -> Adam -> (multicast) in one kernel sequence.  Returns False when this
-        policy/optimizer pair must take the generic path."""
-        from ..optim.adamw import AdamW
-        if self.mode == "ddp" or self.world == 1 or not isinstance(opt, AdamW) or opt.amsgrad or self.f32:
-            return False
-        if not self._synced_any:
-            return False
-        st = self._ensure_opt_state(opt)
-        opt.step_count += 1
-        step_dev = opt._device_step(self.device)
+    def _fused_bucket_step(self, opt, st, b, step_dev):
+        """reduce -> scale -> Adam -> (multicast) for the tensors of bucket b this rank owns; every rank launches (the
+        kernel's flag barriers are collective) whatever it owns."""
+        ext = ops.ext()
         ctx, gbuf, pbuf = (self._solo_ctx, self._solo_g, self._solo_p) if self.comm_stub else (self.comm.ctx, self.G.buf, self.P.buf)
+        hyper = (float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
+                 bool(opt.decoupled), bool(opt.maximize), float(opt.grad_scale * self.scale), self.mode != "zero3", 1,
+                 int(st["bucket_min"][b]))
         if self.fused_rs:
-            if "ranges_rs" not in st:
-                owned_rs = {n: int(n in self.rs_names) for n in st["owned"]}
-                st["ranges_rs"] = [r + [owned_rs[n]] for r, n in zip(st["ranges"], st["owned"])]
             if self.comm_stub and not hasattr(self, "_solo_r"):
-                self._solo_r = ops.ext().SymmBuf([int(self.R.peer_ptrs[self.rank])], 0)
+                self._solo_r = ext.SymmBuf([int(self.R.peer_ptrs[self.rank])], 0)
             rbuf = self._solo_r if self.comm_stub else self.R.buf
-            launches = ops.ext().comm_zero_fused_adam_rs(
-                ctx, gbuf, pbuf, rbuf, st["ranges_rs"], st["master"], st["m"], st["v"],
-                float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
-                bool(opt.decoupled), bool(opt.maximize), float(opt.grad_scale * self.scale),
-                self.mode != "zero3", 1, self._min_launches)
-            ops.count_launch(int(launches))
-            self.stats["fused_steps"] += 1
-            for p in self.params.values():
-                p.grad = None
-            self._accumulated.clear()
-            self._reset_round()
-            self._end_round_zero3()
-            return True
-        launches = ops.ext().comm_zero_fused_adam(
-            ctx, gbuf, pbuf, st["ranges"], st["master"], st["m"], st["v"],
-            float(opt.lr), float(opt.beta1), float(opt.beta2), float(opt.eps), float(opt.weight_decay), step_dev,
-            bool(opt.decoupled), bool(opt.maximize), float(opt.grad_scale * self.scale),
-            self.mode != "zero3", 1, self._min_launches)
+            launches = ext.comm_zero_fused_adam_rs(ctx, gbuf, pbuf, rbuf, st["bucket_ranges"][b], st["master"], st["m"], st["v"],
+                                                   *hyper)
+        else:
+            launches = ext.comm_zero_fused_adam(ctx, gbuf, pbuf, st["bucket_ranges"][b], st["master"], st["m"], st["v"], *hyper)
         ops.count_launch(int(launches))
         self.stats["fused_steps"] += 1
+
+    def fused_optimizer_step(self, opt) -> bool:
+        """ZeRO-1/2/3 + Adam: called from ``optimizer.step()``.  Most buckets already went through their fused
+        reduce -> Adam -> (multicast) kernel during backward; this launches the rest and joins the communication stream.
+        Returns False when this policy/optimizer pair must take the generic path."""
+        if self.mode == "ddp" or not self._fusable(opt):
+            return False
+        if not self._synced_any or self._generic_round:
+            return False
+        self._opt = opt
+        self._flush_zero_buckets()
+        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         for p in self.params.values():
             p.grad = None
         self._accumulated.clear()

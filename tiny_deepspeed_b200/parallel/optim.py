@@ -86,6 +86,9 @@ def _make(base, mode, clsname):
         def __init__(self, named_parameters, *args, param_part_table=None, ranks_map=None, group=None, **kw):
             named = self._setup_sharding(list(named_parameters), param_part_table, ranks_map, group)
             base.__init__(self, named, *args, **kw)
+            pol = self._native_policy()
+            if pol is not None and hasattr(pol, "bind_optimizer"):
+                pol.bind_optimizer(self)      # ZeRO buckets may now run their fused step inside backward
 
     _Opt.__name__ = _Opt.__qualname__ = clsname
     _Opt.__doc__ = f"{base.__name__} for {mode.upper()} (see module docstring)."

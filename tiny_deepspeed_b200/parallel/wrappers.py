@@ -81,7 +81,7 @@ class _ParallelWrapper(tnn.Module):
     def __init__(self, model: tnn.Module, param_part_table: Optional[Dict[str, int]] = None, *,
                  backend: str = "auto", average: bool = False, group=None, device=None,
                  init_seed: int = 0, broadcast_init: bool = True, auto_tune: bool = False,
-                 bucket_bytes: int = 64 << 20):
+                 bucket_bytes: int = 64 << 20, grad_accumulation: bool = False):
         super().__init__()
         self.rank = dist.get_rank(group) if _dist_ready() else 0
         self.world_size = dist.get_world_size(group) if _dist_ready() else 1
@@ -115,7 +115,7 @@ class _ParallelWrapper(tnn.Module):
         if self.backend == "native":
             from .native_policy import NativePolicy
             self.policy = NativePolicy(self.mode, model, table=param_part_table, group=group,
-                                       average=average, bucket_bytes=bucket_bytes)
+                                       average=average, bucket_bytes=bucket_bytes, grad_accumulation=grad_accumulation)
         else:
             self.policy = DistPolicy(self.mode, group=group, average=average)
         wrap_layers(model, self.policy)

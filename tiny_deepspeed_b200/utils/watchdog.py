@@ -1,7 +1,8 @@
 """Failure detection: a host-side watchdog that aborts the process with a diagnostic if a step does not
 complete in time (a peer died, or an in-kernel flag wait would otherwise hang the GPU silently).
-Device-side spin waits in csrc/comm_sm100.cu are bounded as well and raise a sticky error flag that
-``Watchdog.check_device_flags`` reports.  The reference has no failure handling."""
+Device-side spin waits in csrc/comm_sm100.cu are bounded as well (``TDS_COMM_TIMEOUT_S``) and raise a sticky
+error word that :func:`check_device_flags` reports.  ``engine.TrainStep`` arms the watchdog around every step when
+``TDS_WATCHDOG_S`` is set (or ``watchdog_s=`` is passed).  The reference has no failure handling."""
 from __future__ import annotations
 
 import faulthandler
@@ -9,6 +10,19 @@ import os
 import sys
 import threading
 import time
+
+
+def check_device_flags(policy) -> None:
+    """Raise if a device-side collective of ``policy`` (a NativePolicy) timed out.  Reads one int32 from the device, i.e.
+    synchronises with the work queued so far: call it at a step boundary, not inside the hot loop."""
+    comm = getattr(policy, "comm", None)
+    err = getattr(comm, "error", None)
+    if err is None:
+        return
+    if int(err.item()) != 0:
+        rank = os.getenv("RANK", "0")
+        raise RuntimeError(f"[tds] rank {rank}: a device-side collective timed out waiting for a peer "
+                           f"(comm error flag = {int(err.item())}); see the '[tds comm] ... timeout' line above")
 
 
 class Watchdog:
