@@ -79,3 +79,173 @@ def test_broadcast_is_a_noop_for_ddp_and_zero3():
         pol, _ = _stub(mode, 2)
         pol.broadcast_params()
         assert getattr(pol, "_bcast_ranges", None) is None
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# round 2: bucketed ZeRO step inside backward + gradient ring.  The CUDA streams / events / kernels are replaced by
+# recorders so the host-side schedule (which bucket is launched when, with which ranges, which slot waits) runs on CPU.
+# ---------------------------------------------------------------------------------------------------------------------
+class _FakeStream:
+    def __init__(self, name, log):
+        self.name, self.log = name, log
+
+    def wait_stream(self, other):
+        self.log.append(("wait_stream", self.name, other.name))
+
+    def wait_event(self, ev):
+        self.log.append(("wait_event", self.name, ev.tag))
+
+
+class _FakeEvent:
+    n = 0
+
+    def __init__(self, *a, **k):
+        _FakeEvent.n += 1
+        self.tag = _FakeEvent.n
+        self.on = None
+
+    def record(self, stream=None):
+        self.on = getattr(stream, "name", None)
+
+
+class _FakeExt:
+    COMM_MAX_RANGES = 320
+    COMM_MAX_BLOCKS = 128
+
+    def __init__(self, log):
+        self.log = log
+
+    def comm_zero_fused_adam(self, ctx, gbuf, pbuf, ranges, master, m, v, *hyper):
+        self.log.append(("fused", [list(r) for r in ranges], hyper[-1]))
+        return max(1, hyper[-1])
+
+    def step_increment(self, t):
+        t += 1
+
+
+def _policy_for_schedule(monkeypatch, mode, world, rank, bucket_bytes, log):
+    import contextlib
+    from tiny_deepspeed_b200 import ops
+    import tiny_deepspeed_b200 as tds
+    cfg = gpt2_config("tiny", n_layer=3, n_embd=128, n_head=4, vocab_size=1024, block_size=64)
+    with torch.device("meta"):
+        meta = OrderedDict(GPT2Model(cfg).named_parameters())
+        table, _ = partition_tensors(meta, num_parts=world, strategy="balanced")
+    model = GPT2Model(cfg).to(torch.bfloat16)
+    named = list(model.named_parameters())
+    cur = _FakeStream("compute", log)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda dev=None: cur)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "Event", _FakeEvent)
+    fake = _FakeExt(log)
+    monkeypatch.setattr(ops, "ext", lambda: fake)
+    pol = object.__new__(NativePolicy)
+    pol.mode, pol.world, pol.rank, pol.table = mode, world, rank, table
+    pol.device, pol.dtype, pol.f32, pol.esize, pol.scale = torch.device("cpu"), torch.bfloat16, False, 2, 1.0
+    pol.names = [n for n, _ in named]
+    pol.params = OrderedDict(named)
+    pol.shape = {n: tuple(p.shape) for n, p in named}
+    pol.numel = {n: p.numel() for n, p in named}
+    pol._plan_gradient_layout(bucket_bytes, grad_accumulation=False, ring_slots=3)
+    pol.poff, pol.ptotal = dict(pol.foff), pol.ftotal
+    pol.gflat = torch.zeros(pol.gtotal, dtype=torch.bfloat16)
+    pol.pflat = torch.zeros(pol.ptotal, dtype=torch.bfloat16)
+    pol.gview = {n: pol.gflat[pol.goff[n]: pol.goff[n] + pol.numel[n]].view(pol.shape[n]) for n in pol.names}
+    pol._name_of = {id(p): n for n, p in named}
+    pol.comm_stream = _FakeStream("comm", log)
+    pol.comm_stub, pol.fused_rs, pol.rs_names = True, False, frozenset()
+    pol._solo_ctx = pol._solo_g = pol._solo_p = None
+    pol._accumulated, pol._opt_state = set(), None
+    pol.stats = {"allreduce_launches": 0, "fused_steps": 0, "bytes": 0}
+    pol.fetch, pol._seq, pol._seq_frozen, pol._fetched, pol._pos = "push", [], False, {}, 0
+    pol._reset_round()
+    for n, p in named:
+        p._tds_policy, p._tds_name, p.bwd_sync = pol, n, True
+    opt = tds.AdamW(named, lr=1e-3)
+    pol.bind_optimizer(opt)
+    return pol, opt, named, table
+
+
+def test_gradient_ring_layout_never_overlaps_live_buckets():
+    log = []
+    import pytest
+    mp = pytest.MonkeyPatch()
+    try:
+        pol, opt, named, table = _policy_for_schedule(mp, "zero2", 4, 1, 64 << 10, log)
+        assert pol.ring and pol.nslots_g == 3 and len(pol.buckets) > 4
+        assert pol.gtotal == pol.nslots_g * pol.slot_elems < pol.ftotal          # smaller than the full gradient buffer
+        for bi, b in enumerate(pol.buckets):
+            lo = min(pol.goff[n] for n in b)
+            hi = max(pol.goff[n] + _pad(pol.numel[n]) for n in b)
+            slot = bi % pol.nslots_g
+            assert slot * pol.slot_elems <= lo and hi <= (slot + 1) * pol.slot_elems      # a bucket lives in ONE slot
+            spans = sorted((pol.goff[n], pol.goff[n] + _pad(pol.numel[n])) for n in b)
+            assert all(a[1] <= c[0] for a, c in zip(spans, spans[1:]))                    # tensors do not overlap
+        # zero1 keeps the full layout
+        pol1, *_ = _policy_for_schedule(mp, "zero1", 4, 1, 64 << 10, [])
+        assert not pol1.ring and pol1.goff == pol1.foff and pol1.gtotal == pol1.ftotal
+    finally:
+        mp.undo()
+
+
+def test_zero_buckets_step_inside_backward_in_order_with_slot_waits():
+    import pytest
+    mp = pytest.MonkeyPatch()
+    try:
+        for mode in ("zero1", "zero2", "zero3"):
+            log = []
+            pol, opt, named, table = _policy_for_schedule(mp, mode, 4, 2, 64 << 10, log)
+            nb = len(pol.buckets)
+            launched_before_step = 0
+            for n, p in reversed(named):                      # backward visits parameters in reverse registration order
+                out, acc = pol.grad_out(p)
+                assert out.data_ptr() == pol.gview[n].data_ptr() and not acc
+                pol.grad_ready(p, out)
+            launched_before_step = sum(1 for e in log if e[0] == "fused")
+            assert 0 < launched_before_step < nb              # most buckets went during backward, the last ones wait for step()
+            assert pol.fused_optimizer_step(opt) is True
+            fused = [e for e in log if e[0] == "fused"]
+            assert len(fused) == nb                           # every bucket exactly once
+            owned = {n for n in pol.names if table[n] == pol.rank}
+            seen = []
+            for (_, ranges, min_launches), names in zip(fused, pol.buckets):      # launched in bucket order
+                mine = sorted((n for n in names if n in owned), key=lambda k: pol.goff[k])
+                assert [r[0] for r in ranges] == [pol.goff[n] for n in mine]
+                assert [r[3] for r in ranges] == [pol.poff[n] for n in mine]
+                assert min_launches >= 1
+                seen += mine
+            assert sorted(seen) == sorted(owned)              # every owned tensor updated exactly once
+            assert opt.step_count == 1
+            # the compute stream joined the communication stream at the end of the step
+            assert ("wait_stream", "compute", "comm") in log
+            if pol.ring:
+                waits = [e for e in log if e[0] == "wait_event" and e[1] == "compute"]
+                assert len(waits) == nb - pol.nslots_g        # one slot wait per recycled bucket
+            # second round works from a clean state
+            n_before = len([e for e in log if e[0] == "fused"])
+            for n, p in reversed(named):
+                p.bwd_sync = True
+                out, _ = pol.grad_out(p)
+                pol.grad_ready(p, out)
+            assert pol.fused_optimizer_step(opt) is True
+            assert len([e for e in log if e[0] == "fused"]) == 2 * n_before and opt.step_count == 2
+    finally:
+        mp.undo()
+
+
+def test_bucket_runs_merge_adjacent_tensors_of_one_owner():
+    import pytest
+    mp = pytest.MonkeyPatch()
+    try:
+        pol, opt, named, table = _policy_for_schedule(mp, "zero2", 2, 0, 1 << 20, [])
+        for b in range(len(pol.buckets)):
+            runs = pol._bucket_runs(b)
+            flat = [n for _, names in runs for n in names]
+            assert sorted(flat) == sorted(pol.buckets[b])
+            for (o1, n1), (o2, n2) in zip(runs, runs[1:]):
+                adjacent = pol.goff[n1[-1]] + _pad(pol.numel[n1[-1]]) == pol.goff[n2[0]]
+                assert o1 != o2 or not adjacent              # maximal merge
+            for o, names in runs:
+                assert all(table[n] == o for n in names)
+    finally:
+        mp.undo()

@@ -138,19 +138,31 @@ Tensor layernorm_bwd_(const Tensor& dy, const Tensor& x, const Tensor& w, const 
   TORCH_CHECK(dw.scalar_type() == x.scalar_type() && db.scalar_type() == x.scalar_type());
   const int M = x.size(0), N = x.size(1);
   Tensor dx = torch::empty_like(x);
-  Tensor scratch = torch::empty({layernorm_bwd_scratch_rows(), 2 * N}, x.options().dtype(at::kFloat));
   const void* addp = nullptr;
   if (add.has_value() && add->defined()) { TORCH_CHECK(add->is_contiguous() && add->scalar_type() == x.scalar_type()); addp = add->data_ptr(); }
-  // arrival counter of the single-launch fold (the last CTA resets it to zero): one persistent int per device
-  static std::vector<Tensor> counters(64);
+  // TDS_LN_SINGLE=1: single launch — all CTAs reduce their column sums into 8 interleaved persistent, self-cleaning fp32
+  // accumulators (L2 reductions) and the last CTA converts; no fold kernel (25 launches / step less).  Measured on B200
+  // (GPT-2 small step, profiles/r2_step_sweeps.md): 3.46 ms vs 3.40 ms for the default two-kernel form (per-CTA partials +
+  // ln_fold_kernel, deterministic summation order) — 128 CTAs finishing together serialise in the L2 atomic units.
+  static const bool deterministic = !(getenv("TDS_LN_SINGLE") && atoi(getenv("TDS_LN_SINGLE")) != 0);
+  const bool single = !deterministic && x.scalar_type() == at::kBFloat16 && N % 8 == 0 && N <= 2048;
+  static std::vector<Tensor> counters(64), accs(64);
   const int dev = x.get_device();
-  if (!counters[dev].defined()) counters[dev] = torch::zeros({1}, x.options().dtype(at::kInt));
-  // measured (B200, GPT-2 small step): the single-launch variant costs +0.36 ms/step (one CTA folding 128 x 2N partials is
-  // slower than a second, parallel launch), so the two-kernel form is the default; TDS_LN_SINGLE=1 selects the other.
-  static const bool two_kernels = !(getenv("TDS_LN_SINGLE") && atoi(getenv("TDS_LN_SINGLE")) != 0);
+  Tensor scratch;
+  int* counter = nullptr;
+  if (single) {
+    if (!counters[dev].defined()) {
+      counters[dev] = torch::zeros({1}, x.options().dtype(at::kInt));
+      accs[dev] = torch::zeros({8 * 2 * 2048}, x.options().dtype(at::kFloat));   // kAccCopies x 2N
+    }
+    scratch = accs[dev];
+    counter = counters[dev].data_ptr<int>();
+  } else {
+    scratch = torch::empty({layernorm_bwd_scratch_rows(), 2 * N}, x.options().dtype(at::kFloat));
+  }
   layernorm_bwd(dy.data_ptr(), x.data_ptr(), w.data_ptr(), mean.data_ptr<float>(), rstd.data_ptr<float>(), addp,
                 dx.data_ptr(), scratch.data_ptr<float>(), dw.data_ptr(), db.data_ptr(), accumulate, M, N, dtype_of(x),
-                cur_stream(), two_kernels ? nullptr : counters[dev].data_ptr<int>());
+                cur_stream(), counter);
   check_launch("layernorm_bwd");
   return dx;
 }
@@ -335,14 +347,14 @@ void step_increment_(Tensor& step) {
 
 int64_t adamw_multi_(std::vector<Tensor> ps, std::vector<Tensor> gs, std::vector<Tensor> ms, std::vector<Tensor> vs,
                      std::vector<Tensor> masters, std::vector<Tensor> vmax, double lr, double b1, double b2, double eps,
-                     double wd, const Tensor& step, bool decoupled, bool maximize, double grad_scale) {
+                     double wd, const Tensor& step, bool decoupled, bool maximize, double grad_scale, int64_t background_ctas) {
   if (ps.empty()) return 0;
   c10::cuda::CUDAGuard guard(ps[0].device());
   AdamHyper h{(float)lr, (float)b1, (float)b2, (float)eps, (float)wd, (float)grad_scale, decoupled ? 1 : 0,
               maximize ? 1 : 0, step.data_ptr<int>()};
   const int dt = dtype_of(ps[0]);
   int64_t launches = 0;
-  for_each_chunk(ps, gs, ms, vs, masters, vmax, [&](const TensorList& tl) { adamw_multi(tl, h, dt, cur_stream()); ++launches; });
+  for_each_chunk(ps, gs, ms, vs, masters, vmax, [&](const TensorList& tl) { adamw_multi(tl, h, dt, cur_stream(), (int)background_ctas); ++launches; });
   check_launch("adamw_multi");
   return launches;
 }

@@ -18,6 +18,7 @@ void softmax_causal_bwd_generic(const void* p, void* dp_inout, int nmat, int T, 
 //   kernel 2: column-parallel fold of the partials (32 columns x 8 row-lanes per CTA)
 // =====================================================================================================
 constexpr int kRowWarps = 8;
+constexpr int kAccCopies = 8;   // single-launch variant: accumulator copies (scratch holds kAccCopies x 2N floats)
 
 template <int MAXV>
 __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_fast_kernel(
@@ -82,15 +83,29 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_fast_kernel(
   }
   if (first) for (int i = lane; i < 2 * N; i += 32) sdw[i] = 0.f;   // warp had no row
   __syncthreads();
-  float* out = scratch + (size_t)blockIdx.x * 2 * N;
+  if (counter == nullptr) {
+    // two-kernel variant (deterministic summation order): per-CTA partials, ln_fold_kernel finishes the job
+    float* out = scratch + (size_t)blockIdx.x * 2 * N;
+    for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
+      float a = 0.f;
+#pragma unroll
+      for (int k = 0; k < kRowWarps; ++k) a += sm[(size_t)k * 2 * N + i];
+      out[i] = a;
+    }
+    return;
+  }
+  // single-launch variant: every CTA adds its column sums into ONE persistent fp32 accumulator (`scratch`, 2N floats,
+  // zero on entry) with fire-and-forget L2 reductions — 128 CTAs x 2N adds overlap the other CTAs' row work — and the last
+  // CTA to arrive converts the totals to bf16 and leaves accumulator + ticket counter zeroed for the next launch.
+  // (The first attempt let the last CTA fold 128 x 2N partials by itself: +0.36 ms/step, profiles/r1_overlap_pdl.md; this
+  // form is within 0.07 ms/step of the two-kernel default and stays opt-in: TDS_LN_SINGLE=1.)
   for (int i = threadIdx.x; i < 2 * N; i += blockDim.x) {
     float a = 0.f;
 #pragma unroll
     for (int k = 0; k < kRowWarps; ++k) a += sm[(size_t)k * 2 * N + i];
-    out[i] = a;
+    // kAccCopies interleaved accumulators: 128 CTAs adding into ONE address each serialise in the L2 atomic unit
+    atomicAdd(scratch + (size_t)(blockIdx.x % kAccCopies) * 2 * N + i, a);
   }
-  if (counter == nullptr) return;            // two-kernel variant: ln_fold_kernel finishes the job
-  // single-launch variant: the last CTA to arrive folds all per-CTA partials (they are L2-resident: gridDim.x x 2N floats)
   __shared__ int s_last;
   __threadfence();
   __syncthreads();
@@ -98,18 +113,10 @@ __global__ void __launch_bounds__(kRowWarps * 32) ln_bwd_fast_kernel(
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int P = gridDim.x;
   for (int col = threadIdx.x; col < 2 * N; col += blockDim.x) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int r = 0;
-    for (; r + 3 < P; r += 4) {
-      a0 += __ldcg(scratch + (size_t)r * 2 * N + col);
-      a1 += __ldcg(scratch + (size_t)(r + 1) * 2 * N + col);
-      a2 += __ldcg(scratch + (size_t)(r + 2) * 2 * N + col);
-      a3 += __ldcg(scratch + (size_t)(r + 3) * 2 * N + col);
-    }
-    for (; r < P; ++r) a0 += __ldcg(scratch + (size_t)r * 2 * N + col);
-    float t = (a0 + a1) + (a2 + a3);
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < kAccCopies; ++k) { t += __ldcg(scratch + (size_t)k * 2 * N + col); __stcg(scratch + (size_t)k * 2 * N + col, 0.f); }
     __nv_bfloat16* dst = col < N ? dw + col : db + (col - N);
     if (accumulate) t += __bfloat162float(*dst);
     *dst = __float2bfloat16_rn(t);

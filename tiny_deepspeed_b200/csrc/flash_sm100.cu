@@ -28,7 +28,8 @@ namespace {
 
 constexpr int FB = 128;          // query rows per CTA == keys per KV block
 constexpr int HS = 64;           // head size
-constexpr int kFThreads = 192;
+constexpr int kFThreads = 192;       // forward: producer, issuer, 4 softmax warps
+constexpr int kFBThreads = 224;      // backward: + a second MMA issuer (warp 6)
 constexpr uint32_t kTileQK = FB * HS * 2;        // 16 KB: one [128 x 64] bf16 tile
 constexpr uint32_t kTileP = FB * FB * 2;         // 32 KB: P as two K-major 64-column slabs
 constexpr uint32_t kFwdSmem = kTileQK * 5 + kTileP * 2 + 1024 + 256;
@@ -56,13 +57,14 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   const uint32_t tmem_slot = sBar + 8u * NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, so role branches are uniform and issue code can use elect.sync
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int qb = (int)gridDim.x - 1 - (int)blockIdx.x;    // heaviest (last) query blocks are scheduled first
   const int h = blockIdx.y, b = blockIdx.z;
   const int n_kv = qb + 1;
   pdl_launch();
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tma_q); ptx::prefetch_tmap(&tma_k); ptx::prefetch_tmap(&tma_v); ptx::prefetch_tmap(&tma_o);
     ptx::mbar_init(bar(Q_FULL), 1);
     for (int s = 0; s < 2; ++s) {
@@ -82,12 +84,12 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(bar(Q_FULL), kTileQK);
       ptx::tma_load_4d(sQ, &tma_q, bar(Q_FULL), 0, qb * FB, h, b);
       for (int j = 0; j < n_kv; ++j) {
         const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-        ptx::mbar_wait(bar(KV_EMPTY + st), ph ^ 1u);
+        ptx::mbar_wait_conv(bar(KV_EMPTY + st), ph ^ 1u);
         ptx::mbar_expect_tx(bar(KV_FULL + st), 2 * kTileQK);
         ptx::tma_load_4d(sK + st * kTileQK, &tma_k, bar(KV_FULL + st), 0, j * FB, h, b);
         ptx::tma_load_4d(sV + st * kTileQK, &tma_v, bar(KV_FULL + st), 0, j * FB, h, b);
@@ -96,10 +98,10 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   } else if (warp == 1) {
     auto issue_s = [&](int j) {
       const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-      ptx::mbar_wait(bar(KV_FULL + st), ph);
-      ptx::mbar_wait(bar(S_FREE + st), ph ^ 1u);
+      ptx::mbar_wait_conv(bar(KV_FULL + st), ph);
+      ptx::mbar_wait_conv(bar(S_FREE + st), ph ^ 1u);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < HS / 16; ++k) {
           const uint64_t da = ptx::make_smem_desc(sQ + k * 32, 16, 1024);
@@ -110,15 +112,15 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       }
       __syncwarp();
     };
-    ptx::mbar_wait(bar(Q_FULL), 0);
+    ptx::mbar_wait_conv(bar(Q_FULL), 0);
     issue_s(0);
     for (int j = 0; j < n_kv; ++j) {
       if (j + 1 < n_kv) issue_s(j + 1);
       const int st = j & 1; const uint32_t ph = (j >> 1) & 1;
-      ptx::mbar_wait(bar(P_FULL + st), ph);
-      ptx::mbar_wait(bar(PV_FREE + st), ph ^ 1u);
+      ptx::mbar_wait_conv(bar(P_FULL + st), ph);
+      ptx::mbar_wait_conv(bar(PV_FREE + st), ph ^ 1u);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int ks = 0; ks < FB / 16; ++ks) {
           const uint64_t da = ptx::make_smem_desc(sP + st * kTileP + (ks >> 2) * (FB * 128) + (ks & 3) * 32, 16, 1024);
@@ -259,7 +261,7 @@ struct FlashBwdDev {
   uint32_t idesc_s, idesc_dkv, idesc_dq;
 };
 
-__global__ void __launch_bounds__(kFThreads, 1)
+__global__ void __launch_bounds__(kFBThreads, 1)
 flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
                  const __grid_constant__ CUtensorMap tma_dk, const __grid_constant__ CUtensorMap tma_dv,
@@ -273,24 +275,26 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   const uint32_t sDS = sP + kTileP;
   const uint32_t sStg = sDS + kTileP;               // 4 warps x 2 x 4 KB (fp32 dQ halves)
   const uint32_t sBar = sStg + 32768;
-  enum { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, SDP_FULL = 5, SDP_FREE = 6, PDS_FULL = 7, PDS_FREE = 8, DQ_FULL = 9, DQ_FREE = 10, NBAR = 11 };
+  enum { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, SDP_FULL = 5, SDP_FREE = 6, PDS_FULL = 7, PDS_FREE = 8, DQ_FULL = 9, DQ_FREE = 10, DKV_DONE = 11, NBAR = 12 };
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t tmem_slot = sBar + 8u * NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;     // jb = 0 has the most query blocks: scheduled first
   const int nq = g.T / FB;
   const int n_it = nq - jb;
   pdl_launch();
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tma_q); ptx::prefetch_tmap(&tma_k); ptx::prefetch_tmap(&tma_v); ptx::prefetch_tmap(&tma_do);
     ptx::mbar_init(bar(KV_FULL), 1);
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar(QDO_FULL + s), 1); ptx::mbar_init(bar(QDO_EMPTY + s), 1); }
+    // Q / dO stages and the P / dS tiles are read by BOTH issuers: two commits release them
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar(QDO_FULL + s), 1); ptx::mbar_init(bar(QDO_EMPTY + s), 2); }
     ptx::mbar_init(bar(SDP_FULL), 1); ptx::mbar_init(bar(SDP_FREE), 4);
-    ptx::mbar_init(bar(PDS_FULL), 4); ptx::mbar_init(bar(PDS_FREE), 1);
+    ptx::mbar_init(bar(PDS_FULL), 4); ptx::mbar_init(bar(PDS_FREE), 2);
     ptx::mbar_init(bar(DQ_FULL), 1);  ptx::mbar_init(bar(DQ_FREE), 4);
+    ptx::mbar_init(bar(DKV_DONE), 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) { ptx::tmem_alloc(tmem_slot, 512); ptx::tmem_relinquish(); }
@@ -302,27 +306,30 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   pdl_wait();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (ptx::elect_one()) {
       ptx::mbar_expect_tx(bar(KV_FULL), 2 * kTileQK);
       ptx::tma_load_4d(sK, &tma_k, bar(KV_FULL), 0, jb * FB, h, b);
       ptx::tma_load_4d(sV, &tma_v, bar(KV_FULL), 0, jb * FB, h, b);
       for (int it = 0; it < n_it; ++it) {
         const int st = it & 1; const uint32_t ph2 = (it >> 1) & 1;
-        ptx::mbar_wait(bar(QDO_EMPTY + st), ph2 ^ 1u);
+        ptx::mbar_wait_conv(bar(QDO_EMPTY + st), ph2 ^ 1u);
         ptx::mbar_expect_tx(bar(QDO_FULL + st), 2 * kTileQK);
         ptx::tma_load_4d(sQ + st * kTileQK, &tma_q, bar(QDO_FULL + st), 0, (jb + it) * FB, h, b);
         ptx::tma_load_4d(sDO + st * kTileQK, &tma_do, bar(QDO_FULL + st), 0, (jb + it) * FB, h, b);
       }
     }
   } else if (warp == 1) {
-    ptx::mbar_wait(bar(KV_FULL), 0);
+    // ===== issuer A: S = Q K^T, dP = dO V^T (8 MMAs), then dQ = dS K (8 MMAs) =====
+    // One thread issues a tcgen05.mma only every ~80-100 cycles (tools/mma_probe.cu): the 32 MMAs of an (i, j) step cost one
+    // issuer ~2900 cycles against ~1300 cycles of tensor-pipe work, so the step is split between two issuing warps.
+    ptx::mbar_wait_conv(bar(KV_FULL), 0);
     for (int it = 0; it < n_it; ++it) {
       const int st = it & 1; const uint32_t ph2 = (it >> 1) & 1, ph = it & 1;
       const uint32_t q_s = sQ + st * kTileQK, do_s = sDO + st * kTileQK;
-      ptx::mbar_wait(bar(QDO_FULL + st), ph2);
-      ptx::mbar_wait(bar(SDP_FREE), ph ^ 1u);
+      ptx::mbar_wait_conv(bar(QDO_FULL + st), ph2);
+      ptx::mbar_wait_conv(bar(SDP_FREE), ph ^ 1u);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < HS / 16; ++k)
           ptx::mma_f16_ss(tS, ptx::make_smem_desc(q_s + k * 32, 16, 1024), ptx::make_smem_desc(sK + k * 32, 16, 1024),
@@ -334,10 +341,30 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         ptx::mma_commit(bar(SDP_FULL));
       }
       __syncwarp();
-      ptx::mbar_wait(bar(PDS_FULL), ph);
-      ptx::mbar_wait(bar(DQ_FREE), ph ^ 1u);
+      ptx::mbar_wait_conv(bar(PDS_FULL), ph);
+      ptx::mbar_wait_conv(bar(DQ_FREE), ph ^ 1u);
       ptx::tc_fence_after();
-      if (lane == 0) {
+      if (ptx::elect_one()) {
+#pragma unroll
+        for (int k = 0; k < FB / 16; ++k)      // reduction over the 128 keys of block j
+          ptx::mma_f16_ss(tDQ, ptx::make_smem_desc(sDS + (k >> 2) * (FB * 128) + (k & 3) * 32, 16, 1024),
+                          ptx::make_smem_desc(sK + k * 2048, FB * 128, 1024), g.idesc_dq, k > 0 ? 1u : 0u);
+        ptx::mma_commit(bar(DQ_FULL));
+        ptx::mma_commit(bar(QDO_EMPTY + st));     // this thread's S / dP reads of Q, dO have retired (1 of 2 arrivals)
+        ptx::mma_commit(bar(PDS_FREE));           // ... and its dQ read of dS (1 of 2 arrivals)
+      }
+      __syncwarp();
+    }
+  } else if (warp == 6) {
+    // ===== issuer B: dV += P^T dO, dK += dS^T Q (16 MMAs, both operands MN-major) =====
+    ptx::mbar_wait_conv(bar(KV_FULL), 0);
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1; const uint32_t ph2 = (it >> 1) & 1, ph = it & 1;
+      const uint32_t q_s = sQ + st * kTileQK, do_s = sDO + st * kTileQK;
+      ptx::mbar_wait_conv(bar(QDO_FULL + st), ph2);     // TMA-written Q / dO visible to this warp
+      ptx::mbar_wait_conv(bar(PDS_FULL), ph);           // P, dS tiles written by the softmax warps
+      ptx::tc_fence_after();
+      if (ptx::elect_one()) {
 #pragma unroll
         for (int k = 0; k < FB / 16; ++k) {    // reduction over the 128 queries of block i
           const uint32_t acc = (it > 0 || k > 0) ? 1u : 0u;
@@ -346,13 +373,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
           ptx::mma_f16_ss(tDK, ptx::make_smem_desc(sDS + k * 2048, FB * 128, 1024), ptx::make_smem_desc(q_s + k * 2048, FB * 128, 1024),
                           g.idesc_dkv, acc);
         }
-#pragma unroll
-        for (int k = 0; k < FB / 16; ++k)      // reduction over the 128 keys of block j
-          ptx::mma_f16_ss(tDQ, ptx::make_smem_desc(sDS + (k >> 2) * (FB * 128) + (k & 3) * 32, 16, 1024),
-                          ptx::make_smem_desc(sK + k * 2048, FB * 128, 1024), g.idesc_dq, k > 0 ? 1u : 0u);
-        ptx::mma_commit(bar(DQ_FULL));
-        ptx::mma_commit(bar(QDO_EMPTY + st));
-        ptx::mma_commit(bar(PDS_FREE));
+        ptx::mma_commit(bar(QDO_EMPTY + st));     // second arrival: the stage may be refilled
+        ptx::mma_commit(bar(PDS_FREE));           // second arrival: P / dS may be overwritten
+        if (it == n_it - 1) ptx::mma_commit(bar(DKV_DONE));   // dV_j, dK_j complete -> epilogue
       }
       __syncwarp();
     }
@@ -423,6 +446,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       }
     }
     // epilogue: dV_j, dK_j (rows = keys) -> bf16 -> staging -> TMA store into the K / V slices of dqkv
+    ptx::mbar_wait(bar(DKV_DONE), 0);
+    ptx::tc_fence_after();
     if (lane == 0) ptx::bulk_wait_read<0>();
     __syncwarp();
 #pragma unroll
@@ -461,9 +486,18 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 }
 
 // D[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one thread per (b,t,h): 8 x 16-byte loads from each tensor)
+// Also clears the fp32 dQ workspace (8 floats per thread: the grids coincide) — one graph node less per layer than a memset.
 __global__ void flash_dsum_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
-                                  float* __restrict__ dsum, int B, int T, int nh) {
+                                  float* __restrict__ dsum, float* __restrict__ dq_ws, int B, int T, int nh) {
   pdl_launch(); pdl_wait();
+  {
+    const size_t gid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid0 < (size_t)B * T * nh * 8) {
+      float4* z = reinterpret_cast<float4*>(dq_ws) + gid0 * 2;
+      z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+      z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
   // 8 lanes per (b,t,h) row: one 16-byte load from each tensor per lane (fully coalesced), 3-step shuffle reduce
   const int gid = blockIdx.x * blockDim.x + threadIdx.x;
   const int idx = gid >> 3, v8 = gid & 7;
@@ -519,10 +553,10 @@ void flash_bwd(const void* qkv, const void* y, const void* dy, const float* lse,
             make_map(&tdv, view(dbase + 2 * C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, 32) &&
             make_map_f32_2d(&tdq, dq_ws, (int64_t)B * nh * T, HS, HS, 32, 32);
   if (!ok) { fprintf(stderr, "[tds] flash_bwd: tensor map creation failed\n"); abort(); }
-  cudaMemsetAsync(dq_ws, 0, (size_t)B * nh * T * HS * sizeof(float), stream);
+  static_assert(HS == 64, "flash_dsum_kernel clears 8 floats of the dQ workspace per thread (8 threads per row of 64)");
   const int nthreads = B * T * nh * 8;
   launch_k(flash_dsum_kernel, dim3((nthreads + 255) / 256), dim3(256), 0, stream, (const __nv_bfloat16*)dy,
-           (const __nv_bfloat16*)y, dsum, B, T, nh);
+           (const __nv_bfloat16*)y, dsum, dq_ws, B, T, nh);
   FlashBwdDev g;
   g.T = T; g.nh = nh; g.cs = scale * 1.4426950408889634f; g.scale = scale; g.lse = lse; g.dsum = dsum;
   g.idesc_s = make_idesc_bf16(FB, FB, false, false);
@@ -530,7 +564,7 @@ void flash_bwd(const void* qkv, const void* y, const void* dy, const float* lse,
   g.idesc_dq = make_idesc_bf16(FB, HS, false, true);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem); attr = true; }
-  launch_k(flash_bwd_kernel, dim3(T / FB, nh, B), dim3(kFThreads), kBwdSmem, stream, tq, tk, tv, tdo, tdk, tdv, tdq, g);
+  launch_k(flash_bwd_kernel, dim3(T / FB, nh, B), dim3(kFBThreads), kBwdSmem, stream, tq, tk, tv, tdo, tdk, tdv, tdq, g);
   const int nconv = B * nh * T * (HS / 8);
   launch_k(flash_dq_convert_kernel, dim3((nconv + 255) / 256), dim3(256), 0, stream, (const float*)dq_ws, dbase, B, T, nh);
 }

@@ -93,7 +93,7 @@ struct SgdHyper {
   const int* step_ptr;  // momentum buffer is initialised with g when *step_ptr == 1
 };
 void step_increment(int* step_ptr, cudaStream_t s);
-void adamw_multi(const TensorList& tl, const AdamHyper& h, int dtype, cudaStream_t s);
+void adamw_multi(const TensorList& tl, const AdamHyper& h, int dtype, cudaStream_t s, int background_ctas = 0);   // > 0: fixed small grid (optimizer-in-backward)
 void sgd_multi(const TensorList& tl, const SgdHyper& h, int dtype, cudaStream_t s);
 constexpr int kOptChunk = 256 * 8 * 4;   // elements per CTA in the multi-tensor kernels
 

@@ -110,9 +110,69 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const __grid_constant_
   }
 }
 
-void adamw_multi(const TensorList& tl, const AdamHyper& h, int dtype, cudaStream_t s) {
+// Background variant for optimizer-in-backward: a FIXED, small grid (one CTA per SM, 256 threads) walks all chunks.  The
+// flooding kernel above (one CTA per 8192 elements, ~20 k CTAs for GPT-2 small) fills every SM's register file, so a backward
+// GEMM CTA (one per SM, ~32 k registers) launched next to it waits for several of those CTAs to retire — measured in round 1
+// as "overlap buys nothing".  With at most `ctas` resident CTAs of 256 threads the GEMM CTAs always find room and the
+// HBM-bound update streams underneath the latency-bound backward; two packets per thread keep enough bytes in flight.
+template <typename T>
+__global__ void __launch_bounds__(256) adamw_multi_bg_kernel(const __grid_constant__ TensorList tl,
+                                                             const __grid_constant__ AdamHyper h) {
+  pdl_launch(); pdl_wait();
+  const int step = *h.step_ptr;
+  const float bc1 = 1.f - powf(h.beta1, (float)step), bc2r = rsqrtf(1.f - powf(h.beta2, (float)step));
+  const int total = tl.blk_start[tl.count];
+  for (int blk = blockIdx.x; blk < total; blk += gridDim.x) {
+    const int t = find_tensor(tl.blk_start, tl.count, blk);
+    T* p = reinterpret_cast<T*>(tl.p[t]);
+    const T* g = reinterpret_cast<const T*>(tl.g[t]);
+    float* m = tl.m[t];
+    float* v = tl.v[t];
+    float* master = tl.master[t];
+    float* vmax = tl.vmax[t];
+    const int64_t n = tl.numel[t];
+    const int64_t base = (int64_t)(blk - tl.blk_start[t]) * kOptChunk;
+    const int64_t end = base + kOptChunk < n ? base + kOptChunk : n;
+    const bool vec_ok = (n % 4 == 0) && ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g)) % 16 == 0) && !vmax && master;
+    if (vec_ok) {
+      for (int64_t i0 = base + threadIdx.x * 4; i0 < end; i0 += 256 * 4 * 2) {
+        const int64_t i1 = i0 + 256 * 4;
+        const bool two = i1 < end;
+        float w0[4], g0[4], m0[4], v0[4], w1[4], g1[4], m1[4], v1[4];
+        Pk<T>::ld(g + i0, g0); Pk<float>::ld(master + i0, w0); Pk<float>::ld(m + i0, m0); Pk<float>::ld(v + i0, v0);
+        if (two) { Pk<T>::ld(g + i1, g1); Pk<float>::ld(master + i1, w1); Pk<float>::ld(m + i1, m1); Pk<float>::ld(v + i1, v1); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) adam_math(w0[j], g0[j], m0[j], v0[j], nullptr, h, bc1, bc2r);
+        Pk<float>::st(m + i0, m0); Pk<float>::st(v + i0, v0); Pk<float>::st(master + i0, w0); Pk<T>::st(p + i0, w0);
+        if (two) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) adam_math(w1[j], g1[j], m1[j], v1[j], nullptr, h, bc1, bc2r);
+          Pk<float>::st(m + i1, m1); Pk<float>::st(v + i1, v1); Pk<float>::st(master + i1, w1); Pk<T>::st(p + i1, w1);
+        }
+      }
+    } else {
+      for (int64_t i = base + threadIdx.x; i < end; i += 256) {
+        float w = master ? master[i] : ldf(p + i), mm = m[i], vv = v[i];
+        float vx = vmax ? vmax[i] : 0.f;
+        adam_math(w, ldf(g + i), mm, vv, vmax ? &vx : nullptr, h, bc1, bc2r);
+        m[i] = mm; v[i] = vv;
+        if (vmax) vmax[i] = vx;
+        if (master) master[i] = w;
+        stf(p + i, w);
+      }
+    }
+  }
+}
+
+void adamw_multi(const TensorList& tl, const AdamHyper& h, int dtype, cudaStream_t s, int background_ctas) {
   const int blocks = tl.blk_start[tl.count];
   if (blocks == 0) return;
+  if (background_ctas > 0) {
+    const int grid = blocks < background_ctas ? blocks : background_ctas;
+    if (dtype == kBF16) launch_k(adamw_multi_bg_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, s, tl, h);
+    else launch_k(adamw_multi_bg_kernel<float>, dim3(grid), dim3(256), 0, s, tl, h);
+    return;
+  }
   if (dtype == kBF16) launch_k(adamw_multi_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, s, tl, h);
   else launch_k(adamw_multi_kernel<float>, dim3(blocks), dim3(256), 0, s, tl, h);
 }

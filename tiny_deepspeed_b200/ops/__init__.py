@@ -256,7 +256,9 @@ def layernorm_bwd(grad_output, input, weight, mean, rstd, *, dw_out=None, db_out
             accumulate = False
         dx = ext().layernorm_bwd(dy2, x2, weight, mean, rstd, dw_out, db_out, bool(accumulate),
                                  None if add_to_dx is None else _flat2d(add_to_dx))
-        count_launch(1 if os.environ.get("TDS_LN_SINGLE", "0") != "0" else 2)   # row pass + partial fold
+        single = (os.environ.get("TDS_LN_SINGLE", "0") != "0" and dy2.dtype == torch.bfloat16
+                  and dy2.shape[1] % 8 == 0 and dy2.shape[1] <= 2048)
+        count_launch(1 if single else 2)       # single launch (atomic column sums) or row pass + partial fold
         return dx.view_as(input), dw_out, db_out
     dyf, xf = dy2.float(), x2.float()
     xhat = (xf - mean[:, None]) * rstd[:, None]
@@ -510,7 +512,7 @@ def cross_entropy_backward(grad_loss, logits, targets, lse, *, out=None):
 
 def adamw_update(params, grads, exp_avgs, exp_avg_sqs, masters, *, lr, beta1, beta2, eps,
                  weight_decay, step, decoupled=False, maximize=False, grad_scale=1.0,
-                 max_exp_avg_sqs=None, step_dev=None):
+                 max_exp_avg_sqs=None, step_dev=None, background_ctas=0):
     """One fused Adam step over a list of tensors.
 
     Update rule parity: the reference's "AdamW" is Adam with *coupled* L2 (``g += wd*p``,
@@ -522,7 +524,7 @@ def adamw_update(params, grads, exp_avgs, exp_avg_sqs, masters, *, lr, beta1, be
                           masters if masters is not None else [],
                           max_exp_avg_sqs if max_exp_avg_sqs is not None else [],
                           float(lr), float(beta1), float(beta2), float(eps), float(weight_decay),
-                          step_dev, bool(decoupled), bool(maximize), float(grad_scale))
+                          step_dev, bool(decoupled), bool(maximize), float(grad_scale), int(background_ctas))
         count_launch()
         return
     bc1 = 1.0 - beta1 ** step

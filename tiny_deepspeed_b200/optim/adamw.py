@@ -50,4 +50,5 @@ class AdamW(Optimizer):
         ops.adamw_update(ps, gs, ms, vs, masters, lr=self.lr, beta1=self.beta1, beta2=self.beta2,
                          eps=self.eps, weight_decay=self.weight_decay, step=self.step_count,
                          decoupled=self.decoupled, maximize=self.maximize, grad_scale=self.grad_scale,
-                         max_exp_avg_sqs=mx, step_dev=self._device_step(ps[0].device) if ps[0].is_cuda and not ops.is_forced_torch() else None)
+                         max_exp_avg_sqs=mx, step_dev=self._device_step(ps[0].device) if ps[0].is_cuda and not ops.is_forced_torch() else None,
+                         background_ctas=getattr(self, "_background_ctas", 0))

@@ -24,6 +24,8 @@ class StepOverlap:
         self.cur_bytes = 0
         self.closed: List[List[str]] = []
         self.launched_any = False
+        import os
+        self.background_ctas = int(os.environ.get("TDS_OVERLAP_CTAS", "148"))
         self.stats = {"overlapped_buckets": 0, "overlapped_params": 0}
 
     # called by the policy right after a parameter's gradient became final (param.grad is set)
@@ -56,7 +58,12 @@ class StepOverlap:
             opt._device_step(self.device)       # idempotent per step; on the compute stream, before the fork
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream), torch.no_grad():
-            opt._update(names)
+            # overlapped updates run next to backward GEMMs: one CTA per SM so the GEMM CTAs always find room
+            opt._background_ctas = self.background_ctas if overlapped else 0
+            try:
+                opt._update(names)
+            finally:
+                opt._background_ctas = 0
         for n in names:
             p = opt.parameters[n]
             if p.grad is not None and p.grad.is_cuda:

@@ -91,46 +91,7 @@ class NativePolicy(CommPolicy):
         self.params: "OrderedDict[str, torch.nn.Parameter]" = OrderedDict(named)
         self.shape = {n: tuple(getattr(p, "_tds_shape", p.shape)) for n, p in named}
         self.numel = {n: int(torch.Size(self.shape[n]).numel()) for n in self.names}
-        # ---- bucketing: backward produces tensors roughly in reverse registration order ---------------------------------
-        self.buckets: List[List[str]] = []
-        cur, cur_bytes = [], 0
-        for n in reversed(self.names):
-            cur.append(n)
-            cur_bytes += _pad(self.numel[n]) * self.esize
-            if cur_bytes >= bucket_bytes:
-                self.buckets.append(cur)
-                cur, cur_bytes = [], 0
-        if cur:
-            self.buckets.append(cur)
-        self.bucket_of = {n: i for i, b in enumerate(self.buckets) for n in b}
-        # ---- gradient buffer layout ------------------------------------------------------------------------------------
-        # full: every tensor, registration order (DDP, ZeRO-1, or gradient accumulation requested)
-        # ring: ZeRO-2/3 — `nslots` bucket-sized slots recycled during backward (real gradient sharding: a rank never
-        #       holds more than nslots buckets of full gradients + its own reduced shard)
-        self.grad_accumulation = bool(grad_accumulation)
-        # TDS_ZERO_OVERLAP=0: classic schedule (every bucket's step kernel after the last backward kernel) — needs the
-        # full-size buffer, so it also switches the ring off
-        self._zero_overlap = os.environ.get("TDS_ZERO_OVERLAP", "1") != "0"
-        self.ring = mode in ("zero2", "zero3") and self.world > 1 and not self.grad_accumulation and \
-            self._zero_overlap and os.environ.get("TDS_ZERO_RING", "1") != "0"
-        self.foff, off = {}, 0                       # full layout: every tensor, registration order
-        for n in self.names:
-            self.foff[n] = off
-            off += _pad(self.numel[n])
-        self.ftotal = off
-        self.goff = {}
-        if self.ring:
-            self.nslots_g = max(1, min(int(os.environ.get("TDS_RING_SLOTS", ring_slots)), len(self.buckets)))
-            self.slot_elems = max(sum(_pad(self.numel[n]) for n in b) for b in self.buckets)
-            for bi, b in enumerate(self.buckets):
-                off = (bi % self.nslots_g) * self.slot_elems
-                for n in b:
-                    self.goff[n] = off
-                    off += _pad(self.numel[n])
-            self.gtotal = self.nslots_g * self.slot_elems
-        else:
-            self.goff = dict(self.foff)
-            self.gtotal = self.ftotal
+        self._plan_gradient_layout(bucket_bytes, grad_accumulation, ring_slots)
         self.poff = {}                               # parameter buffer
         if mode == "zero3":
             share = [0] * self.world                 # owner-only layout: offsets inside the owner's region
@@ -213,6 +174,51 @@ class NativePolicy(CommPolicy):
         self._solo_ctx = ext.CommCtx([int(self.comm.flags.peer_ptrs[self.rank])], 0, 1, self.comm.error)
         self._solo_g = ext.SymmBuf([int(self.G.peer_ptrs[self.rank])], 0)
         self._solo_p = ext.SymmBuf([int(self.P.peer_ptrs[self.rank])], 0)
+
+    def _plan_gradient_layout(self, bucket_bytes, grad_accumulation=False, ring_slots=3):
+        """Buckets (reverse registration order) and the gradient-buffer layout: full (DDP, ZeRO-1, accumulation) or
+        ring (ZeRO-2/3).  Pure host-side planning: no CUDA, covered by tests/test_native_logic_cpu.py."""
+        import os
+        # ---- bucketing: backward produces tensors roughly in reverse registration order ---------------------------------
+        self.buckets: List[List[str]] = []
+        cur, cur_bytes = [], 0
+        for n in reversed(self.names):
+            cur.append(n)
+            cur_bytes += _pad(self.numel[n]) * self.esize
+            if cur_bytes >= bucket_bytes:
+                self.buckets.append(cur)
+                cur, cur_bytes = [], 0
+        if cur:
+            self.buckets.append(cur)
+        self.bucket_of = {n: i for i, b in enumerate(self.buckets) for n in b}
+        # ---- gradient buffer layout ------------------------------------------------------------------------------------
+        # full: every tensor, registration order (DDP, ZeRO-1, or gradient accumulation requested)
+        # ring: ZeRO-2/3 — `nslots` bucket-sized slots recycled during backward (real gradient sharding: a rank never
+        #       holds more than nslots buckets of full gradients + its own reduced shard)
+        self.grad_accumulation = bool(grad_accumulation)
+        # TDS_ZERO_OVERLAP=0: classic schedule (every bucket's step kernel after the last backward kernel) — needs the
+        # full-size buffer, so it also switches the ring off
+        self._zero_overlap = os.environ.get("TDS_ZERO_OVERLAP", "1") != "0"
+        self.ring = self.mode in ("zero2", "zero3") and self.world > 1 and not self.grad_accumulation and \
+            self._zero_overlap and os.environ.get("TDS_ZERO_RING", "1") != "0"
+        self.foff, off = {}, 0                       # full layout: every tensor, registration order
+        for n in self.names:
+            self.foff[n] = off
+            off += _pad(self.numel[n])
+        self.ftotal = off
+        self.goff = {}
+        if self.ring:
+            self.nslots_g = max(1, min(int(os.environ.get("TDS_RING_SLOTS", ring_slots)), len(self.buckets)))
+            self.slot_elems = max(sum(_pad(self.numel[n]) for n in b) for b in self.buckets)
+            for bi, b in enumerate(self.buckets):
+                off = (bi % self.nslots_g) * self.slot_elems
+                for n in b:
+                    self.goff[n] = off
+                    off += _pad(self.numel[n])
+            self.gtotal = self.nslots_g * self.slot_elems
+        else:
+            self.goff = dict(self.foff)
+            self.gtotal = self.ftotal
 
     def symmetric_bytes(self) -> int:
         """HBM held in symmetric allocations (not visible to torch's caching-allocator statistics)."""
