@@ -251,7 +251,7 @@ def build_ours(args, mode, model_name, rank, world, device):
 
 
 def measure_ours(args, mode, model_name, steps, warmup, rank, local, world, device, *, with_e2e=True, with_exposed=True,
-                 keep=None):
+                 keep=None, check_replicas=False):
     """One config through the public API (TrainStep).  Returns the result dict (same on every rank)."""
     import torch
     import tiny_deepspeed_b200 as tds
@@ -313,6 +313,20 @@ def measure_ours(args, mode, model_name, steps, warmup, rank, local, world, devi
     peak = torch.cuda.max_memory_allocated(device) + symm_bytes       # symmetric (VMM) buffers bypass torch's counters
     peak = max_over_ranks(float(peak), device)
 
+    # ---- replicas bit-identical after the timed steps?  (before the stubbed steps below, whose numerics are meaningless) ----
+    replicas_ok = None
+    if check_replicas and world > 1 and pol is not None and getattr(pol, "mode", "") != "zero3":
+        import torch.distributed as dist
+        h = torch.zeros(2, dtype=torch.int64, device=device)
+        for p in model.parameters():
+            if p.numel():
+                v = p.data.contiguous().view(torch.int16).to(torch.int64)
+                h[0] += v.sum()
+                h[1] += (v * v).sum() % 1_000_003
+        hs = [torch.zeros_like(h) for _ in range(world)]
+        dist.all_gather(hs, h)
+        replicas_ok = all(bool((x == hs[0]).all()) for x in hs)
+
     # ---- exposed (non-overlapped) communication: same step with every collective stubbed out (timing only) --------
     exposed_ms = None
     if with_exposed and world > 1 and hasattr(pol, "comm_stub"):
@@ -338,6 +352,7 @@ def measure_ours(args, mode, model_name, steps, warmup, rank, local, world, devi
         "peak_hbm_bytes": int(peak), "symmetric_bytes": int(symm_bytes), "exposed_comm_ms_per_step": exposed_ms,
         "launches_per_step": int(per_step_launches), "backend": getattr(model, "backend", "local"),
         "cuda_graph": not args.no_graph, "clocks": clk.summary(), "steps": steps, "warmup": warmup,
+        "replicas_bit_identical": replicas_ok,
     }
     if e2e_ms is not None:
         res["e2e"] = {"value": tokens / (e2e_ms * 1e-3), "unit": "tokens/s", "ms_per_step": e2e_ms,
@@ -398,19 +413,6 @@ def comm_check(model, rank, world, device):
             if err > tol:
                 out["ok"] = False
     del flat, buf
-    # replicas bit-identical?  (ZeRO-3 shards parameters: nothing to compare)
-    if pol.mode != "zero3":
-        h = torch.zeros(2, dtype=torch.int64, device=device)
-        for p in pol.params.values():
-            if p.numel():
-                v = p.data.view(torch.int16).to(torch.int64)
-                h[0] += v.sum()
-                h[1] += (v * v).sum() % 1_000_003
-        hs = [torch.zeros_like(h) for _ in range(world)]
-        dist.all_gather(hs, h)
-        same = all(bool((x == hs[0]).all()) for x in hs)
-        out["replicas_bit_identical"] = same
-        out["ok"] = bool(out["ok"] and same)
     return out
 
 
@@ -418,13 +420,18 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
+    os.environ.setdefault("TDS_COMM_TIMEOUT_S", "120")    # a stuck collective must fail this run, not stall it for 10 minutes
     rank, local, world, device = setup_dist(args)
     keep = {}
-    head = measure_ours(args, args.mode, args.model, args.steps, args.warmup, rank, local, world, device, keep=keep)
+    head = measure_ours(args, args.mode, args.model, args.steps, args.warmup, rank, local, world, device, keep=keep,
+                        check_replicas=True)
     check = None
     if world > 1:
         try:
             check = comm_check(keep["model"], rank, world, device)
+            if head.get("replicas_bit_identical") is not None and check.get("ok") is not None:
+                check["replicas_bit_identical"] = head["replicas_bit_identical"]
+                check["ok"] = bool(check["ok"] and head["replicas_bit_identical"])
         except Exception as e:  # pragma: no cover - hardware dependent
             check = {"ok": False, "error": f"{type(e).__name__}: {e}"[:300]}
     keep.clear()

@@ -153,6 +153,7 @@ def _policy_for_schedule(monkeypatch, mode, world, rank, bucket_bytes, log):
     pol.gview = {n: pol.gflat[pol.goff[n]: pol.goff[n] + pol.numel[n]].view(pol.shape[n]) for n in pol.names}
     pol._name_of = {id(p): n for n, p in named}
     pol.comm_stream = _FakeStream("comm", log)
+    pol.step_stream = pol.comm_stream
     pol.comm_stub, pol.fused_rs, pol.rs_names = True, False, frozenset()
     pol._solo_ctx = pol._solo_g = pol._solo_p = None
     pol._accumulated, pol._opt_state = set(), None

@@ -10,6 +10,7 @@
 // Replaces the reference's per-tensor dist.all_reduce / dist.reduce / dist.broadcast + cuda.synchronize()
 // (tiny_deepspeed/core/zero/ddp/module.py:17-24, zero1/module.py:17-24, zero1/optim.py:20-34).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "comm.h"
 #include "common.cuh"
@@ -356,12 +357,23 @@ __global__ void __launch_bounds__(256) zero_fused_adam_kernel(const __grid_const
   block_barrier(c, channel);                       // new parameters visible on every rank
 }
 
+static int step_blocks() {
+  static const int n = [] {
+    const char* e = getenv("TDS_STEP_BLOCKS");
+    int v = e ? atoi(e) : kCommMaxBlocks;
+    return v < 1 ? 1 : (v > kCommMaxBlocks ? kCommMaxBlocks : v);
+  }();
+  return n;
+}
+
 void zero_fused_adam(const CommCtx& c, const SymmBuf& grads, const SymmBuf& params, const OwnedRanges& r, float* master,
                      float* exp_avg, float* exp_avg_sq, const AdamHyper& h, bool bcast_params, int channel,
                      cudaStream_t s) {
   const int work = r.blk_start[r.count];
   // every rank launches the SAME grid (the barrier is per block index), whatever it owns
-  zero_fused_adam_kernel<<<kCommMaxBlocks, 256, 0, s>>>(c, grads, params, r, master, exp_avg, exp_avg_sq, h,
+  // every rank launches the SAME grid (the barrier is per block index), whatever it owns; TDS_STEP_BLOCKS (<= 128) trades the
+  // step kernel's bandwidth against the SM slots it takes from the backward GEMMs it runs under
+  zero_fused_adam_kernel<<<step_blocks(), 256, 0, s>>>(c, grads, params, r, master, exp_avg, exp_avg_sq, h,
                                                         bcast_params ? 1 : 0, channel, work);
 }
 
@@ -457,7 +469,7 @@ void zero_fused_adam_rs(const CommCtx& c, const SymmBuf& grads, const SymmBuf& p
                         float* master, float* exp_avg, float* exp_avg_sq, const AdamHyper& h, bool bcast_params, int channel,
                         cudaStream_t s) {
   const int work = r.r.blk_start[r.r.count];
-  zero_fused_adam_rs_kernel<<<kCommMaxBlocks, 256, 0, s>>>(c, grads, params, rs, r, master, exp_avg, exp_avg_sq, h,
+  zero_fused_adam_rs_kernel<<<step_blocks(), 256, 0, s>>>(c, grads, params, rs, r, master, exp_avg, exp_avg_sq, h,
                                                            bcast_params ? 1 : 0, channel, work);
 }
 

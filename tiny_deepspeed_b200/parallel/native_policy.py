@@ -55,7 +55,7 @@ class NativePolicy(CommPolicy):
     rs_names = frozenset()
 
     def __init__(self, mode: str, model: torch.nn.Module, *, table: Optional[Dict[str, int]] = None, group=None,
-                 average: bool = False, bucket_bytes: int = 64 << 20, comm_blocks: int = 32,
+                 average: bool = False, bucket_bytes: int = 64 << 20, comm_blocks: int = 16,
                  grad_accumulation: bool = False, ring_slots: int = 3):
         self.mode = mode
         self.name = f"native-{mode}"
@@ -69,7 +69,11 @@ class NativePolicy(CommPolicy):
         if os.environ.get("TDS_COMM_BLOCKS"):
             comm_blocks = int(os.environ["TDS_COMM_BLOCKS"])
         self.bucket_bytes = bucket_bytes
+        # collectives that run UNDER backward take few CTAs (measured at 2 GPUs, ddp small: 8 / 16 / 32 / 64 blocks ->
+        # 3.59 / 3.59 / 3.68 / 4.08 ms per step: every SM they sit on slows a single-wave GEMM); the ZeRO-3 parameter
+        # push is on backward's critical path and keeps more requests in flight
         self.comm_blocks = comm_blocks
+        self.push_blocks = int(os.environ.get("TDS_PUSH_BLOCKS", "32"))
         named = [(n, p) for n, p in model.named_parameters()]
         p0 = next(p for _, p in named if p.numel() > 0)
         self.device, self.dtype = p0.device, p0.dtype
@@ -85,6 +89,9 @@ class NativePolicy(CommPolicy):
         import os
         self.comm = symm.Comm(self.device, group)
         self.comm_stream = torch.cuda.Stream(self.device)
+        # ZeRO bucket steps run on their own stream: under ZeRO-3 the communication stream carries the parameter pushes that
+        # backward is waiting for, and a step kernel (Adam over a whole bucket + two cross-GPU barriers) must not delay them
+        self.step_stream = torch.cuda.Stream(self.device) if mode == "zero3" else self.comm_stream
 
         # ---- layout ------------------------------------------------------------------------------
         self.names: List[str] = [n for n, _ in named]
@@ -128,7 +135,8 @@ class NativePolicy(CommPolicy):
         # ---- ZeRO-3 parameter fetch ----------------------------------------------------------------------------
         import os
         self.fetch = os.environ.get("TDS_ZERO3_FETCH", "push")     # "push": owner multicast + prefetch; "peer": GEMM pulls
-        self.lookahead, self.nslots = 2, 4
+        self.lookahead = int(os.environ.get("TDS_ZERO3_LOOKAHEAD", "2"))
+        self.nslots = self.lookahead + 2
         self._seq, self._seq_frozen, self._pos, self._fetched = [], False, 0, {}
         self._groups, self._group_of = [], {}
         if mode == "zero3" and self.fetch == "push" and self.world > 1:
@@ -364,14 +372,14 @@ class NativePolicy(CommPolicy):
                 opt.step_count += 1
                 self._step_opened = True
             step_dev = opt._device_step(self.device)
-        self.comm_stream.wait_stream(cur)
-        with torch.cuda.stream(self.comm_stream):
+        self.step_stream.wait_stream(cur)
+        with torch.cuda.stream(self.step_stream):
             if fused:
                 self._fused_bucket_step(opt, st, b, step_dev)
             else:
                 self._reduce_bucket_to_owners(b)
             ev = torch.cuda.Event()
-            ev.record(self.comm_stream)
+            ev.record(self.step_stream)
         self._bucket_event[b] = ev
         self._launch_order.append(b)
         self._launched[b] = True
@@ -482,7 +490,7 @@ class NativePolicy(CommPolicy):
         elif self.mode != "ddp" and self.world > 1 and self._synced_any and not self._step_opened:
             # generic optimizer: every bucket is reduced onto its owners (most of them already were, during backward)
             self._flush_zero_buckets()
-            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+            torch.cuda.current_stream(self.device).wait_stream(self.step_stream)
             self._accumulated.clear()
             self._reset_round()
             self._end_round_zero3()
@@ -541,7 +549,7 @@ class NativePolicy(CommPolicy):
         with torch.cuda.stream(self.comm_stream):
             if not self.comm_stub:
                 ops.ext().comm_push(self.comm.ctx, int(src), self.S.buf, slot * self.slot_bytes, nbytes, owner,
-                                    self.comm_blocks, 2)
+                                    self.push_blocks, 2)
                 ops.count_launch()
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
@@ -668,7 +676,9 @@ class NativePolicy(CommPolicy):
             return False
         self._opt = opt
         self._flush_zero_buckets()
-        torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
+        torch.cuda.current_stream(self.device).wait_stream(self.step_stream)
+        if self.step_stream is not self.comm_stream:
+            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         for p in self.params.values():
             p.grad = None
         self._accumulated.clear()
