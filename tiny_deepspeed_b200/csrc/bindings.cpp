@@ -130,8 +130,9 @@ std::vector<Tensor> layernorm_fwd_(const Tensor& x, const Tensor& w, const Tenso
   return {y, mean, rstd};
 }
 
+// variant: -1 = TDS_LN_SINGLE decides, 0 = two kernels (partials + fold), 1 = single launch (candidates of the RuntimeAutoTuner)
 Tensor layernorm_bwd_(const Tensor& dy, const Tensor& x, const Tensor& w, const Tensor& mean, const Tensor& rstd,
-                      Tensor& dw, Tensor& db, bool accumulate, const c10::optional<Tensor>& add) {
+                      Tensor& dw, Tensor& db, bool accumulate, const c10::optional<Tensor>& add, int64_t variant) {
   check_cuda(x, "x");
   c10::cuda::CUDAGuard guard(x.device());
   TORCH_CHECK(dy.is_contiguous() && x.is_contiguous() && w.is_contiguous() && dw.is_contiguous() && db.is_contiguous());
@@ -145,7 +146,8 @@ Tensor layernorm_bwd_(const Tensor& dy, const Tensor& x, const Tensor& w, const 
   // (GPT-2 small step, profiles/r2_step_sweeps.md): 3.46 ms vs 3.40 ms for the default two-kernel form (per-CTA partials +
   // ln_fold_kernel, deterministic summation order) — 128 CTAs finishing together serialise in the L2 atomic units.
   static const bool deterministic = !(getenv("TDS_LN_SINGLE") && atoi(getenv("TDS_LN_SINGLE")) != 0);
-  const bool single = !deterministic && x.scalar_type() == at::kBFloat16 && N % 8 == 0 && N <= 2048;
+  const bool want_single = variant < 0 ? !deterministic : variant == 1;
+  const bool single = want_single && x.scalar_type() == at::kBFloat16 && N % 8 == 0 && N <= 2048;
   static std::vector<Tensor> counters(64), accs(64);
   const int dev = x.get_device();
   Tensor scratch;
@@ -385,7 +387,9 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.def("set_gemm_pair", &set_gemm_pair, "route eligible GEMMs through the cta_group::2 kernel (0/1)");
   m.def("gemm_set_prof", &gemm_set_prof_t, "install / clear the per-CTA phase timestamp buffer (tools/gemm_timeline.py)");
   m.def("layernorm_fwd", &layernorm_fwd_);
-  m.def("layernorm_bwd", &layernorm_bwd_);
+  m.def("layernorm_bwd", &layernorm_bwd_, pybind11::arg("dy"), pybind11::arg("x"), pybind11::arg("w"), pybind11::arg("mean"),
+        pybind11::arg("rstd"), pybind11::arg("dw"), pybind11::arg("db"), pybind11::arg("accumulate"), pybind11::arg("add"),
+        pybind11::arg("variant") = -1);
   m.def("embedding_fwd", &embedding_fwd_);
   m.def("embedding_bwd", &embedding_bwd_);
   m.def("softmax_causal_fwd", &softmax_causal_fwd_);

@@ -220,7 +220,8 @@ class _LayerNormFn(torch.autograd.Function):
             wacc = False
         dx, dw, db = ops.layernorm_bwd(dy.contiguous(), x, w, mean, rstd, dw_out=wo, db_out=bo,
                                        accumulate=wacc,
-                                       add_to_dx=dres.contiguous() if dres is not None else None)
+                                       add_to_dx=dres.contiguous() if dres is not None else None,
+                                       runtime_tuner=getattr(module, "runtime_tuner", None))
         pol.release(weight, w)
         pol.grad_ready(weight, dw)
         pol.grad_ready(bias, db)

@@ -158,7 +158,9 @@ def _gemm_tuned(tuner, key, a, b, **kw):
     if tuner is None or not getattr(tuner, "enable", False) or not on_gpu(a, b) or kw.get("accumulate"):
         return gemm(a, b, **kw)
     import functools
-    cands = [functools.partial(gemm, config=c) for c in (None, 0, 1, 2)]
+    n_out = (b.shape[-1] if kw.get("b_mn") else b.shape[-2])
+    configs = [None, 0, 1, 2] + ([3] if n_out % 192 == 0 else [])      # BN = heuristic, 64, 128, 256, 192
+    cands = [functools.partial(gemm, config=c) for c in configs]
     return tuner.choose_function(cands, a, b, key=key, **kw)
 
 
@@ -244,7 +246,7 @@ def layernorm_fwd(input, weight, bias, eps=1e-5, runtime_tuner=None):
 
 
 def layernorm_bwd(grad_output, input, weight, mean, rstd, *, dw_out=None, db_out=None,
-                  accumulate=False, add_to_dx=None):
+                  accumulate=False, add_to_dx=None, runtime_tuner=None):
     """Fused LayerNorm backward: ``dx`` plus ``dw``/``db`` (two launches on GPU: row pass with
     per-CTA fp32 partials — no global spin-lock unlike reference ops/layernorm.py:257-269 — and a
     column reduce).  ``add_to_dx`` fuses the residual-branch gradient add."""
@@ -254,10 +256,20 @@ def layernorm_bwd(grad_output, input, weight, mean, rstd, *, dw_out=None, db_out
             dw_out = torch.empty_like(weight)
             db_out = torch.empty_like(weight)
             accumulate = False
-        dx = ext().layernorm_bwd(dy2, x2, weight, mean, rstd, dw_out, db_out, bool(accumulate),
-                                 None if add_to_dx is None else _flat2d(add_to_dx))
-        single = (os.environ.get("TDS_LN_SINGLE", "0") != "0" and dy2.dtype == torch.bfloat16
-                  and dy2.shape[1] % 8 == 0 and dy2.shape[1] <= 2048)
+        add2 = None if add_to_dx is None else _flat2d(add_to_dx)
+        fast = dy2.dtype == torch.bfloat16 and dy2.shape[1] % 8 == 0 and dy2.shape[1] <= 2048
+        variant = -1                                                   # -1: TDS_LN_SINGLE decides (default two kernels)
+        tuner = runtime_tuner
+        if tuner is not None and getattr(tuner, "enable", False) and fast and not accumulate:
+            # the tuner picks between the two-kernel form (per-CTA partials + fold) and the single-launch form (L2 reductions
+            # + last-CTA finish) per (rows, width) — reference ops/layernorm.py:82-127 threads its tuner through the same op
+            import functools
+            cands = [functools.partial(ext().layernorm_bwd, variant=v) for v in (0, 1)]
+            dx = tuner.choose_function(cands, dy2, x2, weight, mean, rstd, dw_out, db_out, False, add2, key="layernorm_bwd")
+            variant = tuner.best("layernorm_bwd", dy2, x2, weight, mean, rstd, dw_out, db_out, False, add2)
+        else:
+            dx = ext().layernorm_bwd(dy2, x2, weight, mean, rstd, dw_out, db_out, bool(accumulate), add2, -1)
+        single = fast and (variant == 1 or (variant == -1 and os.environ.get("TDS_LN_SINGLE", "0") != "0"))
         count_launch(1 if single else 2)       # single launch (atomic column sums) or row pass + partial fold
         return dx.view_as(input), dw_out, db_out
     dyf, xf = dy2.float(), x2.float()

@@ -676,9 +676,8 @@ class NativePolicy(CommPolicy):
             return False
         self._opt = opt
         self._flush_zero_buckets()
+        # (the ZeRO-3 push stream needs no join here: every push was consumed through its event by the layer that used it)
         torch.cuda.current_stream(self.device).wait_stream(self.step_stream)
-        if self.step_stream is not self.comm_stream:
-            torch.cuda.current_stream(self.device).wait_stream(self.comm_stream)
         for p in self.params.values():
             p.grad = None
         self._accumulated.clear()

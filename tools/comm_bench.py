@@ -64,14 +64,19 @@ def main():
         iters = 20 if nbytes < (100 << 20) else 8
         for blocks in (32, 128):
             t = timeit(lambda: comm.allreduce(st, 0, n, blocks=blocks, channel=3), iters, dev, sync)
-            # NVLS two-shot: a GPU sends its contribution to (N-1)/N of the buffer and receives (N-1)/N of the result
-            rows.append(("all-reduce (ours, %d blocks)" % blocks, label, t, nbytes, nbytes * f, nbytes * f / t / 1e3))
+            # NVLS two-shot, per GPU and direction: multimem.ld_reduce makes every GPU send its copy of ALL slices to the
+            # switch (S out, its own slice included) and receive its reduced slice (S/N in); multimem.st sends that slice
+            # (S/N out) and receives every slice (S in)  ->  S (1 + 1/N) each way
+            wire = nbytes * (1 + 1 / world)
+            rows.append(("all-reduce (ours NVLS two-shot, %d blocks)" % blocks, label, t, nbytes, wire, wire / t / 1e3))
         t = timeit(lambda: dist.all_reduce(nccl_buf[:n]), iters, dev, sync)
-        rows.append(("all-reduce (NCCL)", label, t, nbytes, nbytes * f, nbytes * f / t / 1e3))
+        wire = nbytes * (1 + 1 / world)     # same accounting (NCCL picks NVLS / ring itself; ring moves 2 (N-1)/N S)
+        rows.append(("all-reduce (NCCL)", label, t, nbytes, wire, wire / t / 1e3))
         t = timeit(lambda: comm.reduce_to(st, 0, n, world - 1, blocks=128, channel=3), iters, dev, sync)
-        rows.append(("reduce-to-owner (ours)", label, t, nbytes, nbytes * f, nbytes * f / t / 1e3))     # the owner receives (N-1) x S / N ... via the switch: S
+        # switch-side reduction: every GPU sends S, the owner receives S
+        rows.append(("reduce-to-owner (ours, multimem.ld_reduce)", label, t, nbytes, nbytes, nbytes / t / 1e3))
         t = timeit(lambda: dist.reduce(nccl_buf[:n], dst=world - 1), iters, dev, sync)
-        rows.append(("reduce (NCCL)", label, t, nbytes, nbytes * f, nbytes * f / t / 1e3))
+        rows.append(("reduce (NCCL)", label, t, nbytes, nbytes, nbytes / t / 1e3))
         t = timeit(lambda: comm.broadcast(st, 0, nbytes, 0, blocks=128, channel=3), iters, dev, sync)
         rows.append(("broadcast / multicast (ours)", label, t, nbytes, nbytes, nbytes / t / 1e3))
         t = timeit(lambda: dist.broadcast(nccl_buf[:n], src=0), iters, dev, sync)
@@ -88,9 +93,10 @@ def main():
     t = timeit(lambda: ext.comm_zero_fused_adam(comm.ctx, st.buf, P.buf, ranges, master, m, v, 1e-5, 0.9, 0.999, 1e-8, 0.1, step,
                                                 False, False, 1.0, True, 3, 1), 8, dev, sync)
     tot = n * world * 2
-    # per GPU: sends (N-1)/N of its gradient buffer into the switch reduction, receives (N-1)/N of the new parameters;
-    # local HBM: 28 B x S/N of optimizer state traffic
-    rows.append(("ZeRO fused reduce->Adam->multicast (ours)", "326 MB grads + params", t, tot, tot * f, tot * f / t / 1e3))
+    # per GPU and direction: S out (gradient copies into the switch reduction) + S/N out (its new parameters), S/N in
+    # (reduced gradients) + S in (everyone's new parameters); local HBM: 28 B x S/N of optimizer state traffic
+    wire = tot * (1 + 1 / world)
+    rows.append(("ZeRO fused reduce->Adam->multicast (ours)", "326 MB grads + 326 MB params", t, tot, wire, wire / t / 1e3))
     if rank == 0:
         print(f"## native collectives on {world} x B200 (device-timed, max over ranks)\n")
         print("| collective | message | time us | algorithmic bytes | NVLink bytes / GPU / direction | GB/s / direction | of 770 GB/s |")
