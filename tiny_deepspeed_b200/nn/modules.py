@@ -255,7 +255,7 @@ class _EmbeddingFn(torch.autograd.Function):
     @_traced("embedding.fwd")
     def forward(ctx, idx, weight, module, add):
         pol = policy_of(module)
-        w = pol.acquire(weight)
+        w = pol.acquire(weight, sparse=True)          # ZeRO-3: a gather touches <= ntokens rows of a [V, D] table
         y = ops.embedding_forward(idx, w, module.padding_idx, module.max_norm, module.norm_type,
                                   module.scale_grad_by_freq, module.sparse, add=add)
         pol.release(weight, w)

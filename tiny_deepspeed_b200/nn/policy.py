@@ -19,8 +19,9 @@ class CommPolicy:
     name = "base"
 
     # ---- parameters (ZeRO-3) -----------------------------------------------------------
-    def acquire(self, param: torch.nn.Parameter, *, backward: bool = False) -> torch.Tensor:
-        """Return the full tensor to compute with (gathers it for a non-resident ZeRO-3 param)."""
+    def acquire(self, param: torch.nn.Parameter, *, backward: bool = False, sparse: bool = False) -> torch.Tensor:
+        """Return the full tensor to compute with (gathers it for a non-resident ZeRO-3 param).  ``sparse``: the
+        consumer reads only a few rows (embedding gather) — a policy may hand out a remote alias instead of a copy."""
         return param
 
     def release(self, param: torch.nn.Parameter, full: torch.Tensor) -> None:

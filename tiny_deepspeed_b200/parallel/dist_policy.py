@@ -92,7 +92,7 @@ class DistPolicy(CommPolicy):
             self._retire_one()
 
     # ---------------------------------------------------------------- parameters (ZeRO-3)
-    def acquire(self, param, *, backward=False):
+    def acquire(self, param, *, backward=False, sparse=False):
         if self.mode != "zero3" or self.world == 1:
             return param
         owner = param.rank_id

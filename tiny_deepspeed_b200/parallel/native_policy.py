@@ -496,11 +496,18 @@ class NativePolicy(CommPolicy):
             self._end_round_zero3()
 
     # ------------------------------------------------------------------------------------------ ZeRO-3 parameters
-    def acquire(self, param, *, backward=False):
+    def acquire(self, param, *, backward=False, sparse=False):
         if self.mode != "zero3" or self.world == 1:
             return param
         n = self._name_of[id(param)]
         owner = self._owner(n)
+        if sparse and owner != self.rank:
+            # embedding gather: <= ntokens rows of a [V, D] table (1.5 MB of the 77 MB wte for GPT-2 small) — the gather
+            # kernel reads them straight from the owner's memory over NVLink instead of waiting for a push of the whole
+            # table at the very start of forward, where nothing can hide it
+            return self.P.peer(owner, self.shape[n], self.dtype, self.poff[n] * self.esize)
+        if sparse:
+            return param.data
         if self.fetch == "peer":
             if owner == self.rank:
                 return param.data
