@@ -118,8 +118,8 @@ __device__ __forceinline__ float ld1_any(const void* base, long long idx, int f3
 // EPI  = epilogue functor fixed at compile time (EPI_*), or -1: read g.epi at run time (generic instantiations)
 // FAST = the output goes registers -> swizzled smem -> TMA store and nothing else is compiled in (bf16 out, aligned, no
 //        accumulate: every GEMM of the bf16 training step); the generic instantiations keep the direct-store paths
-template <int BN, bool F32, bool RED, bool DUAL, int EPI, bool FAST>
-__global__ void __launch_bounds__(DUAL ? kThreadsDual : kThreads, 1)
+template <int BN, bool F32, bool RED, int NP, int EPI, bool FAST>
+__global__ void __launch_bounds__(32 * (2 * NP + 4), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
             const __grid_constant__ GemmDev g) {
@@ -127,10 +127,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   long long* const prof = kProf ? g.prof : nullptr;     // compile-time nullptr in production builds
   const int dbg = kProf ? g.dbg : 0;
   const int epi = EPI >= 0 ? EPI : g.epi;
-  constexpr int kHalves = DUAL ? 2 : 1;
+  constexpr bool DUAL = NP > 1;
+  constexpr int kHalves = NP;                           // k-interleaved pipelines ("halves" when NP = 2)
+  static_assert(2 * NP * BN <= 512, "two accumulator stages of NP x BN fp32 columns must fit TMEM");
   constexpr int kSH = C::kStages / kHalves;            // ring stages per pipeline
   constexpr int kAccCols = kHalves * BN;               // TMEM columns of one accumulator stage
-  constexpr int kEpiWarp0 = DUAL ? 4 : 2;              // first epilogue warp
+  constexpr uint32_t kTmemAlloc = 2 * kAccCols <= 128 ? 128u : (2 * kAccCols <= 256 ? 256u : 512u);   // power of two
+  constexpr int kEpiWarp0 = 2 * NP;                    // first epilogue warp (4 consecutive warps cover the 4 TMEM lane quadrants)
   constexpr int kBK = F32 ? 32 : BK;     // K elements per stage = one 128-byte row
   constexpr int kGrp = F32 ? 32 : 64;    // MN elements per 128-byte row of an MN-major operand
   extern __shared__ uint8_t smem_raw[];
@@ -172,7 +175,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
-    ptx::tmem_alloc(tmem_slot, DUAL ? C::kTmemColsDual : C::kTmemCols);
+    ptx::tmem_alloc(tmem_slot, kTmemAlloc);
     ptx::tmem_relinquish();
   }
   ptx::tc_fence_before();
@@ -192,9 +195,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const int nkb = (g.K + kBK - 1) / kBK;
 
   // half-K pipeline this warp belongs to (DUAL): warps 0/1 = half 0, warps 2/3 = half 1
-  const int half = DUAL ? (warp >> 1) & 1 : 0;
-  const bool is_producer = DUAL ? (warp == 0 || warp == 2) : warp == 0;
-  const bool is_issuer = DUAL ? (warp == 1 || warp == 3) : warp == 1;
+  // warps 2p / 2p+1 = (TMA producer, MMA issuer) of pipeline p, which owns the k-blocks kb0 + p, kb0 + p + NP, ...
+  const int half = warp < 2 * NP ? (warp >> 1) : 0;
+  const bool is_producer = warp < 2 * NP && (warp & 1) == 0;
+  const bool is_issuer = warp < 2 * NP && (warp & 1) == 1;
   const int s0 = half * kSH;                           // this pipeline's slice of the smem ring
 
   if (is_producer) {
@@ -342,17 +346,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const bool row_ok = m < g.M;
       const long long d_off = (long long)b1 * g.dbs1 + (long long)b2 * g.dbs2 + (long long)m * g.ldd;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + as * kAccCols;
-      // DUAL: D = D0 + D1 (even + odd k-blocks); D1 is untouched when the tile's K range holds a single k-block
-      bool two = false;
-      if (DUAL) { int kb0, kb1; tile_k_range<kBK>(g, m0, nkb, kb0, kb1); two = kb0 + 1 < kb1; }
+      // NP > 1: D = sum of the pipelines' accumulators; pipeline p is untouched when the tile's K range has <= p k-blocks
+      int npipe = 1;
+      if (DUAL) { int kb0, kb1; tile_k_range<kBK>(g, m0, nkb, kb0, kb1); npipe = kb1 - kb0 < NP ? kb1 - kb0 : NP; }
       auto ld_acc = [&](uint32_t col, uint32_t (&raw)[32]) {
         ptx::tmem_ld_32x32(t_row + col, raw);
-        if (DUAL && two) {
-          uint32_t hi[32];
-          ptx::tmem_ld_32x32(t_row + BN + col, hi);
-          ptx::tmem_ld_wait();
+        if (DUAL && npipe > 1) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(hi[j]));
+          for (int p = 1; p < NP; ++p) {
+            if (p < npipe) {
+              uint32_t hi[32];
+              ptx::tmem_ld_32x32(t_row + p * BN + col, hi);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) raw[j] = __float_as_uint(__uint_as_float(raw[j]) + __uint_as_float(hi[j]));
+            }
+          }
         } else {
           ptx::tmem_ld_wait();
         }
@@ -585,7 +594,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   if (g.cm > 1) ptx::cluster_sync();   // nobody leaves while a peer may still multicast into / signal this CTA
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc(tmem_base, DUAL ? C::kTmemColsDual : C::kTmemCols);
+    ptx::tmem_dealloc(tmem_base, kTmemAlloc);
   }
 }
 
@@ -697,22 +706,22 @@ static int max_clusters(int cm) {
   at[0].val.clusterDim.x = cm; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
   cfg.attrs = at; cfg.numAttrs = 1;
   int n = 0;
-  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false, false, false, -1, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<BN, false, false, 1, -1, false>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = g_num_sms / cm / 2; }
   cache[cm] = n;
   return n;
 }
 
-template <int BN, bool F32, bool RED = false, bool DUAL = false, int EPI = -1, bool FAST = false>
+template <int BN, bool F32, bool RED = false, int NP = 1, int EPI = -1, bool FAST = false>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                    const GemmDev& g, int tiles, cudaStream_t s) {
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(gemm_kernel<BN, F32, RED, DUAL, EPI, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
+    cudaFuncSetAttribute(gemm_kernel<BN, F32, RED, NP, EPI, FAST>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<BN>::kSmem);
     attr_done = true;
   }
   if (g.cm == 1) {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    launch_k(gemm_kernel<BN, F32, RED, DUAL, EPI, FAST>, dim3(grid), dim3(DUAL ? kThreadsDual : kThreads), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
+    launch_k(gemm_kernel<BN, F32, RED, NP, EPI, FAST>, dim3(grid), dim3(32 * (2 * NP + 4)), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
     return;
   }
   // cluster launch: cm consecutive CTAs = cm consecutive M tiles of one N tile; grid is a whole number of clusters
@@ -721,7 +730,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   if (clusters > cap) clusters = cap;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * g.cm);
-  cfg.blockDim = dim3(DUAL ? kThreadsDual : kThreads);
+  cfg.blockDim = dim3(32 * (2 * NP + 4));
   cfg.dynamicSmemBytes = Cfg<BN>::kSmem;
   cfg.stream = s;
   cudaLaunchAttribute at[2];
@@ -730,7 +739,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = at; cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32, RED, DUAL, EPI, FAST>, ta, tb, td, tx, g);
+  cudaLaunchKernelEx(&cfg, gemm_kernel<BN, F32, RED, NP, EPI, FAST>, ta, tb, td, tx, g);
 }
 
 // cluster size along M: B-tile multicast divides L2->SM (or NVLink, for a ZeRO-3 peer weight) operand traffic by cm
@@ -803,15 +812,25 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
     }
     g.tma_store = ok ? 1 : 0;
   }
-  // two half-K pipelines per CTA whenever the MMA is narrow enough to be issue-bound (BN <= 128, bf16)
+  static const int dual_env = getenv("TDS_GEMM_DUAL") ? atoi(getenv("TDS_GEMM_DUAL")) : 1;   // 0: one pipeline per CTA
   const int T = (int)tiles;
-#define TDS_L(BN_, F32_, RED_, DUAL_, EPI_, FAST_) launch<BN_, F32_, RED_, DUAL_, EPI_, FAST_>(ta, tb, td, tx, g, T, stream)
-#define TDS_BY_BN(F32_, RED_, EPI_, FAST_)                                           \
-  do {                                                                               \
-    if (cfg == 0) TDS_L(64, F32_, RED_, !(F32_), EPI_, FAST_);                       \
-    else if (cfg == 1) TDS_L(128, F32_, RED_, !(F32_), EPI_, FAST_);                 \
-    else if (cfg == 2) TDS_L(256, F32_, RED_, false, EPI_, FAST_);                   \
-    else TDS_L(192, F32_, RED_, false, EPI_, FAST_);                                 \
+#define TDS_L(BN_, F32_, RED_, NP_, EPI_, FAST_) launch<BN_, F32_, RED_, NP_, EPI_, FAST_>(ta, tb, td, tx, g, T, stream)
+  // pipelines per CTA: BN = 64 -> 4 (its MMAs are 32-48 cycles of tensor work against ~80-100 cycles of issue per thread),
+  // BN = 128 -> 2 (64 cycles: two issuers already saturate the pipe), wider tiles and fp32 -> 1.  g_variant (harness only):
+  // 1 = single pipeline everywhere, 2 = at most two pipelines.
+#define TDS_BY_BN(F32_, RED_, EPI_, FAST_)                                                        \
+  do {                                                                                            \
+    const int np64 = (F32_) || g_variant == 1 || !dual_env ? 1 : (g_variant == 2 || (RED_) ? 2 : 4);   \
+    const int np128 = (F32_) || g_variant == 1 || !dual_env ? 1 : 2;                              \
+    if (cfg == 0) {                                                                               \
+      if (np64 == 4) TDS_L(64, F32_, RED_, (F32_) || (RED_) ? 1 : 4, EPI_, FAST_);               \
+      else if (np64 == 2) TDS_L(64, F32_, RED_, (F32_) ? 1 : 2, EPI_, FAST_);                    \
+      else TDS_L(64, F32_, RED_, 1, EPI_, FAST_);                                                \
+    } else if (cfg == 1) {                                                                        \
+      if (np128 == 2) TDS_L(128, F32_, RED_, (F32_) ? 1 : 2, EPI_, FAST_);                       \
+      else TDS_L(128, F32_, RED_, 1, EPI_, FAST_);                                               \
+    } else if (cfg == 2) TDS_L(256, F32_, RED_, 1, EPI_, FAST_);                                 \
+    else TDS_L(192, F32_, RED_, 1, EPI_, FAST_);                                                 \
   } while (0)
   if (p.reduce_out) {
     TDS_BY_BN(false, true, -1, false);
