@@ -455,3 +455,41 @@ def test_native_zero_checkpoint_roundtrip(tmp_path):
         assert r["step"] == 6 and r["n_state"] > 0 and r["has_moments"], r
         assert r["resumed_step"] == 7, r
         assert r["l_resumed"] == pytest.approx(r["l_next"], rel=2e-3, abs=2e-3), r
+
+
+def _ddp_sparse_embedding(rank, world, sparse):
+    """DDP with / without the row-sparse all-reduce of the token-embedding gradient: every touched row goes through the same
+    switch reduction + multicast as in the dense kernel, so the two runs must agree bit for bit."""
+    import os
+    os.environ["TDS_SPARSE_EMB"] = "1" if sparse else "0"
+    import tiny_deepspeed_b200 as tds
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    from tiny_deepspeed_b200.parallel import materialize_
+    dev = torch.device("cuda", rank)
+    cfg = gpt2_config("tiny", n_layer=2, n_embd=256, n_head=4, vocab_size=8192, block_size=128)
+    with torch.device("meta"):
+        model = GPT2Model(cfg).to(torch.bfloat16)
+    materialize_(model, device=dev, seed=5)
+    model = tds.DDP(model, backend="native", bucket_bytes=1 << 20)
+    opt = tds.DDPAdamW(model.named_parameters(), lr=1e-3, weight_decay=0.1)
+    g = torch.Generator().manual_seed(50 + rank)
+    x = torch.randint(0, cfg.vocab_size, (2, 128), generator=g).to(dev)
+    x[0, :8] = 7                                            # repeated ids inside a rank ...
+    y = torch.randint(0, cfg.vocab_size, (2, 128), generator=g).to(dev)
+    x[1, :4] = 11 + 0 * rank                                # ... and the same id on every rank
+    step = tds.TrainStep(model, opt, use_graph=True, warmup=2)
+    losses = [float(step(x, y)) for _ in range(6)]
+    final = {n: p.detach().float().cpu() for n, p in model.module.named_parameters()}
+    return losses, final, dict(model.policy.stats)
+
+
+def test_ddp_row_sparse_embedding_allreduce_is_bit_identical_to_dense():
+    world = _world()
+    sp = run_gpu_distributed(_ddp_sparse_embedding, world=world, args=(True,), timeout=300)
+    de = run_gpu_distributed(_ddp_sparse_embedding, world=world, args=(False,), timeout=300)
+    assert sp[0][2].get("sparse_allreduce_launches", 0) > 0 and de[0][2].get("sparse_allreduce_launches", 0) == 0
+    assert sp[0][0] == de[0][0], (sp[0][0], de[0][0])
+    for n in sp[0][1]:
+        assert torch.equal(sp[0][1][n], de[0][1][n]), n
+        for r in range(1, world):
+            assert torch.equal(sp[r][1][n], sp[0][1][n]), (n, r)       # replicas stay bit-identical

@@ -35,6 +35,14 @@ void broadcast_from(const CommCtx& c, const SymmBuf& buf, int64_t byte_off, int6
 // rank src pushes nbytes from its LOCAL pointer into dst[dst_byte_off ...) on every rank (ZeRO-3 parameter fetch)
 void push_from(const CommCtx& c, const void* src_local, const SymmBuf& dst, int64_t dst_byte_off, int64_t nbytes,
                int src_rank, int blocks, int channel, cudaStream_t s);
+// every rank multicasts ITS slot [base + rank * slot_bytes, + slot_bytes) of buf to all ranks (slot_bytes % 16 == 0)
+void allgather_slots(const CommCtx& c, const SymmBuf& buf, int64_t base_byte_off, int64_t slot_bytes, int blocks, int channel,
+                     cudaStream_t s);
+// row-sparse bf16 all-reduce of the [vocab, row_bytes] table at table_byte_off: only the rows named in ids[0, nids) (duplicates
+// allowed; identical list on every rank), each reduced once by rank row % world.  epoch_of_row: int[vocab], never cleared;
+// *epoch_ptr must differ from the previous call's value (the optimizer's device step counter).
+void allreduce_rows(const CommCtx& c, const SymmBuf& buf, int64_t table_byte_off, int64_t row_bytes, const int64_t* ids, int nids,
+                    int64_t vocab, int* epoch_of_row, const int* epoch_ptr, int blocks, int channel, cudaStream_t s);
 // cross-GPU barrier (all blocks of all ranks)
 void barrier(const CommCtx& c, int channel, cudaStream_t s);
 

@@ -65,6 +65,20 @@ void py_push(const PyComm& c, int64_t src_ptr, const PyBuf& dst, int64_t dst_byt
             (int)channel, cur_stream());
   check_launch("push");
 }
+void py_allgather_slots(const PyComm& c, const PyBuf& b, int64_t base_byte_off, int64_t slot_bytes, int64_t blocks, int64_t channel) {
+  TORCH_CHECK(slot_bytes % 16 == 0 && base_byte_off % 16 == 0, "allgather_slots: 16-byte aligned slots");
+  allgather_slots(c.ctx, b.buf, base_byte_off, slot_bytes, (int)blocks, (int)channel, cur_stream());
+  check_launch("allgather_slots");
+}
+void py_allreduce_rows(const PyComm& c, const PyBuf& b, int64_t table_byte_off, int64_t row_bytes, const Tensor& ids, int64_t vocab,
+                       Tensor epoch_of_row, const Tensor& epoch, int64_t blocks, int64_t channel) {
+  TORCH_CHECK(ids.is_cuda() && ids.scalar_type() == at::kLong && ids.is_contiguous(), "ids: contiguous int64 CUDA tensor");
+  TORCH_CHECK(epoch_of_row.scalar_type() == at::kInt && epoch_of_row.numel() >= vocab && epoch.scalar_type() == at::kInt);
+  TORCH_CHECK(row_bytes % 16 == 0 && table_byte_off % 16 == 0, "allreduce_rows: 16-byte aligned rows");
+  allreduce_rows(c.ctx, b.buf, table_byte_off, row_bytes, ids.data_ptr<int64_t>(), (int)ids.numel(), vocab,
+                 epoch_of_row.data_ptr<int>(), epoch.data_ptr<int>(), (int)blocks, (int)channel, cur_stream());
+  check_launch("allreduce_rows");
+}
 void py_barrier(const PyComm& c, int64_t channel) {
   barrier(c.ctx, (int)channel, cur_stream());
   check_launch("barrier");
@@ -155,6 +169,8 @@ void bind_comm(pybind11::module_& m) {
   m.def("comm_broadcast", &py_broadcast);
   m.def("comm_barrier", &py_barrier);
   m.def("comm_push", &py_push);
+  m.def("comm_allgather_slots", &py_allgather_slots);
+  m.def("comm_allreduce_rows", &py_allreduce_rows);
   m.def("comm_zero_fused_adam", &py_zero_fused_adam);
   m.def("comm_zero_fused_adam_rs", &py_zero_fused_adam_rs);
   m.attr("COMM_MAX_BLOCKS") = kCommMaxBlocks;

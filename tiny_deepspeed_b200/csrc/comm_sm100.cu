@@ -235,6 +235,11 @@ __global__ void __launch_bounds__(kCommThreads) push_kernel(const __grid_constan
   block_barrier(c, channel);   // every rank has released the slot's previous contents
   if (c.rank == src_rank) {
     constexpr int U = 4;
+    // Two ranks: plain stores into the one peer.  A multicast store is replicated to EVERY member of the group, the source
+    // included, so at world = 2 half of the owner's inbound NVLink bandwidth would carry its own data back (measured on GPT-2 XL
+    // ZeRO-3: the echo doubles the 3.3 GB of parameter traffic each rank receives per step); from 4 ranks up the switch-side
+    // replication (owner egress 1x instead of (N-1)x) wins.
+    const bool unicast = dst.mc == nullptr || c.world == 2;
     const long long stride = (long long)gridDim.x * blockDim.x * U;
     for (long long base = (long long)blockIdx.x * blockDim.x * U + threadIdx.x; base < nvec; base += stride) {
       uint4 v[U];
@@ -243,7 +248,12 @@ __global__ void __launch_bounds__(kCommThreads) push_kernel(const __grid_constan
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const long long i = base + (long long)u * blockDim.x;
-        if (i < nvec) bcast_vec(c, dst, (size_t)(dst_boff + i * 16), v[u]);
+        if (i >= nvec) continue;
+        if (unicast) {
+          for (int r = 1; r < c.world; ++r) st16((char*)dst.peer[(c.rank + r) % c.world] + dst_boff + i * 16, v[u]);   // the owner reads its own parameters in place
+        } else {
+          mm_st((char*)dst.mc + dst_boff + i * 16, v[u]);
+        }
       }
     }
   }
@@ -256,6 +266,72 @@ void push_from(const CommCtx& c, const void* src_local, const SymmBuf& dst, int6
   if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
   push_kernel<<<blocks, kCommThreads, 0, s>>>(c, (const char*)src_local, dst, (long long)dst_byte_off,
                                              (long long)((nbytes + 15) / 16), src_rank, channel);
+}
+
+// =====================================================================================================
+// Row-sparse all-reduce of an embedding gradient (DDP).  Backward touches at most `ntok` rows per rank of the [V, D]
+// table (1024 of 50304 for GPT-2 small): instead of all-reducing 77 MB of mostly zeros at the very end of backward, the
+// ranks exchange their token ids (kernel 1: every rank multicasts its ids into its slot of a symmetric buffer) and then
+// all-reduce only the touched rows (kernel 2).  Every row is reduced EXACTLY once, by the rank `row % world`, with the
+// same switch reduction + multicast store as the dense kernel, so all replicas receive identical bits; rows nobody
+// touched stay zero on every rank (each rank zero-fills its own dense gradient before the scatter).
+// A per-row epoch word (never cleared: the epoch is the optimizer step) deduplicates ids that occur several times.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) allgather_slots_kernel(const __grid_constant__ CommCtx c,
+                                                              const __grid_constant__ SymmBuf b, long long base_boff,
+                                                              long long slot_vecs, int channel) {
+  block_barrier(c, channel);                       // every rank has filled its own slot (stream order) and nobody still reads
+  const long long my0 = base_boff + (long long)c.rank * slot_vecs * 16;
+  const char* local = (const char*)b.peer[c.rank];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < slot_vecs; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 v = *reinterpret_cast<const uint4*>(local + my0 + i * 16);
+    bcast_vec(c, b, (size_t)(my0 + i * 16), v);
+  }
+  __threadfence_system();
+  block_barrier(c, channel);                       // all slots visible everywhere
+}
+
+void allgather_slots(const CommCtx& c, const SymmBuf& buf, int64_t base_byte_off, int64_t slot_bytes, int blocks, int channel,
+                     cudaStream_t s) {
+  if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
+  allgather_slots_kernel<<<blocks, 256, 0, s>>>(c, buf, (long long)base_byte_off, (long long)(slot_bytes / 16), channel);
+}
+
+// ids: world * ntok gathered token ids (int64, identical on every rank); one warp per gathered id
+__global__ void __launch_bounds__(256) allreduce_rows_kernel(const __grid_constant__ CommCtx c,
+                                                             const __grid_constant__ SymmBuf b, long long table_boff,
+                                                             int row_vecs, const long long* __restrict__ ids, int nids,
+                                                             long long vocab, int* __restrict__ epoch_of_row,
+                                                             const int* __restrict__ epoch_ptr, int channel) {
+  block_barrier(c, channel);                       // every rank's scatter-add into its dense gradient is complete
+  const int epoch = *epoch_ptr;
+  const int lane = threadIdx.x & 31;
+  const int warp = (int)((blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5);
+  const int nwarps = (int)((gridDim.x * (long long)blockDim.x) >> 5);
+  for (int e = warp; e < nids; e += nwarps) {
+    const long long id = ids[e];
+    if (id < 0 || id >= vocab || (int)(id % c.world) != c.rank) continue;       // rows are dealt round-robin to the ranks
+    int won = 0;
+    if (lane == 0) won = atomicExch(epoch_of_row + id, epoch) != epoch;          // first occurrence of this row in this step
+    won = __shfl_sync(0xffffffffu, won, 0);
+    if (!won) continue;
+    const size_t row = (size_t)table_boff + (size_t)id * (size_t)row_vecs * 16;
+    for (int v = lane; v < row_vecs; v += 32) {
+      float f[8];
+      reduce_vec<false>(c, b, row + (size_t)v * 16, f);
+      bcast_vec(c, b, row + (size_t)v * 16, pack_bf16x8(f));
+    }
+  }
+  __threadfence_system();
+  block_barrier(c, channel);                       // reduced rows visible on every rank
+}
+
+void allreduce_rows(const CommCtx& c, const SymmBuf& buf, int64_t table_byte_off, int64_t row_bytes, const int64_t* ids, int nids,
+                    int64_t vocab, int* epoch_of_row, const int* epoch_ptr, int blocks, int channel, cudaStream_t s) {
+  if (blocks > kCommMaxBlocks) blocks = kCommMaxBlocks;
+  allreduce_rows_kernel<<<blocks, 256, 0, s>>>(c, buf, (long long)table_byte_off, (int)(row_bytes / 16),
+                                               reinterpret_cast<const long long*>(ids), nids, (long long)vocab, epoch_of_row,
+                                               epoch_ptr, channel);
 }
 
 __global__ void barrier_kernel(const __grid_constant__ CommCtx c, int channel) { block_barrier(c, channel); }

@@ -30,11 +30,14 @@ def _traced(name):
     return deco
 
 
-def _grad_of(policy, param, compute):
+def _grad_of(policy, param, compute, rows=None):
     """Run ``compute(out, accumulate) -> grad`` into the policy's buffer and publish the result."""
     out, acc = policy.grad_out(param)
     g = compute(out, acc)
-    policy.grad_ready(param, g)
+    if rows is None:
+        policy.grad_ready(param, g)
+    else:
+        policy.grad_ready(param, g, rows=rows)
 
 
 # dW || dX: the two GEMMs of a Linear's backward are independent and, at 1x1024 tokens, each is a single under-filled
@@ -274,7 +277,7 @@ class _EmbeddingFn(torch.autograd.Function):
         dy = dy.contiguous()
         _grad_of(pol, weight, lambda out, acc: ops.embedding_weight_grad(
             idx, dy, weight, module.padding_idx, out=out, accumulate=acc,
-            shape=(module.num_embeddings, module.embedding_dim)))
+            shape=(module.num_embeddings, module.embedding_dim)), rows=idx)
         dadd = None
         if ctx.add_shape is not None and ctx.needs_input_grad[3]:
             dadd = dy

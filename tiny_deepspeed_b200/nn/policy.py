@@ -32,10 +32,11 @@ class CommPolicy:
         """Where the backward kernel should write ``d(param)``: ``(buffer or None, accumulate)``."""
         return None, False
 
-    def grad_ready(self, param: torch.nn.Parameter, grad: torch.Tensor) -> None:
+    def grad_ready(self, param: torch.nn.Parameter, grad: torch.Tensor, rows: Optional[torch.Tensor] = None) -> None:
         """``grad`` (this micro-batch's gradient, or the running sum if it was accumulated into the
         buffer from :meth:`grad_out`) is complete: publish it as ``param.grad`` and start the
-        collective that this mode attaches to it."""
+        collective that this mode attaches to it.  ``rows``: for an embedding table, the token ids whose rows are the only
+        non-zero ones of ``grad`` (lets a policy reduce just those rows)."""
         raise NotImplementedError
 
     def finish(self) -> None:
@@ -48,7 +49,7 @@ class LocalPolicy(CommPolicy):
     name = "local"
     overlap = None        # optional optim.overlap.StepOverlap (set by engine.TrainStep)
 
-    def grad_ready(self, param, grad):
+    def grad_ready(self, param, grad, rows=None):
         if param.grad is None:
             param.grad = grad
         elif param.grad.data_ptr() != grad.data_ptr():

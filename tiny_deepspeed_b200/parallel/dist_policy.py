@@ -51,7 +51,7 @@ class DistPolicy(CommPolicy):
         else:
             param._tds_grad = g   # a ZeRO-3 non-owner has no storage to hang .grad on; the grad is transient anyway
 
-    def grad_ready(self, param, grad):
+    def grad_ready(self, param, grad, rows=None):
         prev = self._get(param)
         if prev is not None and prev.data_ptr() != grad.data_ptr():
             prev.add_(grad)

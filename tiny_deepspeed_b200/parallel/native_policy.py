@@ -170,6 +170,8 @@ class NativePolicy(CommPolicy):
                 loc._tds_reduce = True
                 view._tds_reduce = True
                 self._rs_local[n], self._rs_view[n] = loc, view
+        self._sparse_emb = os.environ.get("TDS_SPARSE_EMB", "1") != "0" and mode == "ddp" and self.world > 1
+        self._sparse_state = {}
         self._reset_round()
         self._accumulated = set()      # names holding un-synced micro-batch gradients
         self._opt_state = None
@@ -256,6 +258,7 @@ class NativePolicy(CommPolicy):
         self._zero_deferred = []          # complete ZeRO buckets waiting for one more grad_ready (their dX GEMMs)
         self._slot_waited = [False] * len(self.buckets)
         self._generic_round = False       # a bucket of this round went through the generic reduce-to-owner path
+        self._rows = {}                   # DDP: embedding tables whose gradient is row-sparse this round -> token ids
 
     def _owner(self, name):
         return self.table[name]
@@ -286,7 +289,7 @@ class NativePolicy(CommPolicy):
             self._wait_slot(self.bucket_of[n])
         return self.gview[n], (n in self._accumulated)
 
-    def grad_ready(self, param, grad):
+    def grad_ready(self, param, grad, rows=None):
         n = self._name_of[id(param)]
         if self.fused_rs and n in self.rs_names:               # already on its way to the owner
             if getattr(param, "bwd_sync", False):
@@ -299,6 +302,7 @@ class NativePolicy(CommPolicy):
                 self.gview[n].add_(grad)
             else:
                 self.gview[n].copy_(grad)
+        fresh = n not in self._accumulated                     # no earlier micro-batch accumulated into this buffer
         self._accumulated.add(n)
         owner_like = self.mode in ("ddp", "zero1") or self._owner(n) == self.rank
         if owner_like and param.numel() > 0 and not self.ring:
@@ -315,6 +319,8 @@ class NativePolicy(CommPolicy):
         if self.mode == "ddp":
             b = self.bucket_of[n]
             self._ready[b] += 1
+            if rows is not None and self._sparse_ok(n, rows, fresh):
+                self._rows[n] = rows                   # only these rows of the table's gradient are non-zero
             # the all-reduce only touches the gradient buffer, so a bucket can go the moment its last dW is enqueued;
             # it then runs on the comm stream underneath the remaining dX/dW GEMMs of backward
             # optimizer-in-backward: buckets whose all-reduce was queued at an EARLIER grad_ready can be updated now
@@ -434,23 +440,65 @@ class NativePolicy(CommPolicy):
                 # the flush at the end of backward has the GPU to itself: use every comm block the flag pad allows
                 self._launch_bucket(b, blocks=ops.ext().COMM_MAX_BLOCKS if flush else None)
 
+    # ---- DDP: row-sparse all-reduce of embedding gradients ----------------------------------------------------------
+    def _sparse_ok(self, n, rows, fresh) -> bool:
+        """Reduce only the touched rows of table `n`?  bf16, plain SUM, no accumulated micro-batches, and the rows of all
+        ranks together cover at most a quarter of the table (wte: 8 x 1024 of 50304 rows; wpe: every row -> dense)."""
+        if not self._sparse_emb or self.f32 or self.scale != 1.0 or not fresh or self.comm_stub:
+            return False
+        shape = self.shape[n]
+        return (len(shape) == 2 and shape[1] % 8 == 0 and rows.numel() % 2 == 0 and rows.dtype == torch.int64
+                and self.world * rows.numel() * 4 <= shape[0])
+
+    def _sparse_allreduce(self, n, rows, blocks):
+        """On the communication stream: all-gather the token ids, then switch-reduce + multicast only the touched rows."""
+        ext = ops.ext()
+        ntok = rows.numel()
+        st = self._sparse_state.get(n)
+        if st is None or st["ntok"] != ntok:
+            ids = symm.alloc(self.world * ntok * 8, self.device, self.group)
+            st = dict(ntok=ntok, ids=ids, flat=ids.local.view(torch.int64),
+                      epoch_of_row=torch.zeros(self.shape[n][0], dtype=torch.int32, device=self.device),
+                      epoch=torch.zeros(1, dtype=torch.int32, device=self.device))
+            self._sparse_state[n] = st
+        st["flat"][self.rank * ntok: (self.rank + 1) * ntok].copy_(rows.reshape(-1))
+        ext.comm_allgather_slots(self.comm.ctx, st["ids"].buf, 0, ntok * 8, 4, 0)
+        ext.step_increment(st["epoch"])
+        ext.comm_allreduce_rows(self.comm.ctx, self.G.buf, self.goff[n] * self.esize, self.shape[n][1] * self.esize,
+                                st["flat"][: self.world * ntok], self.shape[n][0], st["epoch_of_row"], st["epoch"],
+                                int(blocks), 0)
+        ops.count_launch(3)
+        self.stats["sparse_allreduce_launches"] = self.stats.get("sparse_allreduce_launches", 0) + 1
+        self.stats["bytes"] += self.world * ntok * (8 + self.shape[n][1] * self.esize)
+
     def _launch_bucket(self, b, blocks=None):
         names = self.buckets[b]
-        lo = min(self.goff[n] for n in names)
-        hi = max(self.goff[n] + _pad(self.numel[n]) for n in names)
+        # embedding tables with a row list leave the dense range when they sit at one end of it (wte is the first tensor of
+        # the flat layout, i.e. the low end of the last bucket)
+        dense = sorted(names, key=lambda k: self.goff[k])
+        sparse = []
+        while dense and dense[0] in self._rows:
+            sparse.append(dense.pop(0))
+        while dense and dense[-1] in self._rows:
+            sparse.append(dense.pop())
         cur = torch.cuda.current_stream(self.device)
         self.comm_stream.wait_stream(cur)
         with torch.cuda.stream(self.comm_stream):
             if not self.comm_stub:
-                self.comm.allreduce(self.G, lo, hi - lo, f32=self.f32, scale=self.scale, blocks=blocks or self.comm_blocks,
-                                    channel=0)
+                if dense:
+                    lo = min(self.goff[n] for n in dense)
+                    hi = max(self.goff[n] + _pad(self.numel[n]) for n in dense)
+                    self.comm.allreduce(self.G, lo, hi - lo, f32=self.f32, scale=self.scale, blocks=blocks or self.comm_blocks,
+                                        channel=0)
+                    self.stats["bytes"] += (hi - lo) * self.esize
+                for n in sparse:
+                    self._sparse_allreduce(n, self._rows[n], blocks or self.comm_blocks)
             ev = torch.cuda.Event()
             ev.record(self.comm_stream)
         self._bucket_event[b] = ev
         self._launch_order.append(b)
         self._launched[b] = True
         self.stats["allreduce_launches"] += 1
-        self.stats["bytes"] += (hi - lo) * self.esize
 
     def flush_async(self):
         """DDP: queue the all-reduce of the last (still open) buckets WITHOUT joining the communication stream and
