@@ -170,7 +170,10 @@ class NativePolicy(CommPolicy):
                 loc._tds_reduce = True
                 view._tds_reduce = True
                 self._rs_local[n], self._rs_view[n] = loc, view
-        self._sparse_emb = os.environ.get("TDS_SPARSE_EMB", "1") != "0" and mode == "ddp" and self.world > 1
+        # row-sparse all-reduce of embedding gradients: validated (replicas stay bit-identical) but opt-in — at 2 GPUs it costs
+        # 3.72 vs 3.60 ms/step: the dense 77 MB all-reduce of the last bucket already hides under the early Adam update, while
+        # the sparse path adds four small latency-bound kernels (id copy, id all-gather, epoch bump, row reduce) to the tail
+        self._sparse_emb = os.environ.get("TDS_SPARSE_EMB", "0") != "0" and mode == "ddp" and self.world > 1
         self._sparse_state = {}
         self._reset_round()
         self._accumulated = set()      # names holding un-synced micro-batch gradients
