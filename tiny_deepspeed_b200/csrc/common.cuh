@@ -100,16 +100,20 @@ template <typename T> TDS_DEVICE void stf(T* p, float v);
 template <> TDS_DEVICE void stf<float>(float* p, float v) { *p = v; }
 template <> TDS_DEVICE void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
+// One MUFU instruction (max relative error ~2^-11, well inside bf16's 2^-8 rounding of every value it feeds) instead of
+// tanhf's ~40-instruction two-branch sequence: the GELU epilogues run on the GEMM's 4 epilogue warps only, 192 elements per
+// thread for a 128 x 192 tile, and were issue-bound on exactly that sequence (profiles/r2_timeline.md).
+TDS_DEVICE float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 TDS_DEVICE float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float u = k0 * (x + k1 * x * x * x);
-  return 0.5f * x * (1.f + tanhf(u));
+  return 0.5f * x * (1.f + tanh_fast(u));
 }
 TDS_DEVICE float gelu_tanh_grad(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;
   float x2 = x * x;
   float u = k0 * (x + k1 * x * x2);
-  float t = tanhf(u);
+  float t = tanh_fast(u);
   return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * k0 * (1.f + 3.f * k1 * x2);
 }
 

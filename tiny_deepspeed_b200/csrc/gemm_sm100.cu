@@ -57,6 +57,7 @@ struct GemmDev {
   int dbg;      // TDS_GEMM_DBG bits (profiling only): 1 = no global stores, 2 = no MMA issue, 4 = no epilogue body
   uint32_t idesc;
   long long* prof;   // per-CTA phase timestamps (16 x int64 per CTA), nullptr outside tools/gemm_timeline.py
+  const char* pf; long long pf_bytes;   // L2 prefetch hint for the next kernel's operand (GemmParams::prefetch)
 };
 
 // Phase stamps / debug bits exist only in builds with -DTDS_GEMM_PROF (tools/build_harness.sh): the production kernels carry
@@ -78,7 +79,10 @@ template <int BN> struct Cfg {
   static constexpr int kStages = BN == 256 ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : 8));
   static constexpr int kABytes = BM * BK * 2;   // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
-  static constexpr int kSmem = kStages * (kABytes + kBBytes) + 4 * 2 * 4096 /*epilogue staging*/ + 1024 /*align*/ + 256 /*barriers*/;
+  // epilogue staging: kEpiBufs 4 KB slabs per epilogue warp.  BN = 192 has the room for 4 (its 3 slabs of a residual / GELU'
+  // aux tile are all prefetched during the main loop; GELU+save alternates two (output, pre-activation) pairs)
+  static constexpr int kEpiBufs = BN == 192 ? 4 : 2;
+  static constexpr int kSmem = kStages * (kABytes + kBBytes) + 4 * kEpiBufs * 4096 /*epilogue staging*/ + 1024 /*align*/ + 512 /*barriers*/;
   static constexpr int kTmemCols = BN == 64 ? 128 : (BN == 128 ? 256 : 512);   // power of two >= 2 * BN
   static constexpr int kTmemColsDual = BN == 64 ? 256 : 512;                   // 2 accumulator stages x 2 half-K accumulators
 };
@@ -140,15 +144,16 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sA = smem_base;
   const uint32_t sB = smem_base + C::kStages * C::kABytes;
-  const uint32_t sStage = sB + C::kStages * C::kBBytes;              // 4 warps x 2 x (32 rows x 128 B), 1024-aligned
-  const uint32_t sBar = sStage + 4u * 2u * kStageBufBytes;
+  constexpr int NB = C::kEpiBufs;
+  const uint32_t sStage = sB + C::kStages * C::kBBytes;              // 4 warps x NB x (32 rows x 128 B), 1024-aligned
+  const uint32_t sBar = sStage + 4u * (uint32_t)NB * kStageBufBytes;
   // barrier layout (8 B each): full[kStages], empty[kStages], tmem_full[2], tmem_empty[2], then tmem ptr
   auto full_bar = [&](int s) { return sBar + 8u * s; };
   auto empty_bar = [&](int s) { return sBar + 8u * (C::kStages + s); };
   auto tfull_bar = [&](int s) { return sBar + 8u * (2 * C::kStages + s); };
   auto tempty_bar = [&](int s) { return sBar + 8u * (2 * C::kStages + 2 + s); };
   const uint32_t tmem_slot = sBar + 8u * (2 * C::kStages + 4);
-  auto aux_bar = [&](int w) { return sBar + 8u * (2 * C::kStages + 6 + w); };   // per epilogue warp: aux tile landed
+  auto aux_bar = [&](int w, int i) { return sBar + 8u * (2 * C::kStages + 6 + w * 4 + i); };   // per epilogue warp and staging buffer: aux slab landed
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot_ptr =
       reinterpret_cast<volatile uint32_t*>(smem_gen + (tmem_slot - smem_base));
@@ -171,7 +176,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // cm MMA issuers have released it
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (uint32_t)g.cm); }
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), kHalves); ptx::mbar_init(tempty_bar(s), 4); }
-    for (int w = 0; w < 4; ++w) ptx::mbar_init(aux_bar(w), 1);
+    for (int w = 0; w < 4; ++w)
+      for (int i = 0; i < NB; ++i) ptx::mbar_init(aux_bar(w, i), 1);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -325,10 +331,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
     int local = 0;
     uint32_t sbuf_toggle = 0;
-    const uint32_t my_stage0 = sStage + (uint32_t)q * 2u * kStageBufBytes;   // two 4 KB staging buffers per warp
+    const uint32_t my_stage0 = sStage + (uint32_t)q * (uint32_t)NB * kStageBufBytes;   // NB 4 KB staging buffers per warp
     const bool gelu_save = epi == EPI_GELU_SAVE;
-    const bool aux_in = g.aux_tma && (epi == EPI_GELU_BWD || epi == EPI_RESIDUAL);   // aux tile arrives by TMA
-    uint32_t aux_phase = 0;
+    // aux tile (residual / pre-activation) arrives by TMA: always on the FAST kernels (the host only picks them when the aux
+    // tensor map exists), a runtime property on the generic ones
+    const bool aux_in = (FAST || g.aux_tma) && (epi == EPI_GELU_BWD || epi == EPI_RESIDUAL);
+    uint32_t aux_phase = 0;                       // bit i: parity of aux_bar(q, i)
+    if (g.pf) {
+      // these four warps have nothing to do until the first accumulator is complete: spread the next kernel's weight
+      // (or saved activation) over all CTAs in 4 KB requests and pull it from HBM into L2 underneath this main loop
+      constexpr long long kChunk = 4096;
+      const long long nchunk = (g.pf_bytes + kChunk - 1) / kChunk;
+      const int e = (warp - kEpiWarp0) * 32 + lane;
+      for (long long c = (long long)blockIdx.x + (long long)gridDim.x * e; c < nchunk; c += (long long)gridDim.x * 128) {
+        const long long left = g.pf_bytes - c * kChunk;
+        ptx::prefetch_l2_bulk(g.pf + c * kChunk, (uint32_t)(left < kChunk ? left : kChunk));
+      }
+    }
     const bool vec_ok = (g.N % 8 == 0) && (g.ldd % 8 == 0) && ((reinterpret_cast<uintptr_t>(g.d) & 15) == 0) &&
                         (g.aux == nullptr || (g.ld_aux % 8 == 0 && (reinterpret_cast<uintptr_t>(g.aux) & 15) == 0));
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -339,6 +358,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       const int as = local & 1;
       const uint32_t aphase = (local >> 1) & 1;
       ++local;
+      // residual / pre-activation slabs (32 rows x 64 cols each) of this tile: fetched by TMA into the staging buffers NOW, while
+      // the main loop is still running, instead of one exposed load latency per slab after it (slab s -> buffer s % NB;
+      // the result is written back in place and TMA-stored from the same buffer)
+      int n_slabs = 0;
+      if ((FAST || g.tma_store) && !RED) {
+        n_slabs = (g.N - n0 + 63) / 64;
+        if (n_slabs > BN / 64) n_slabs = BN / 64;
+        if (dbg & 4) n_slabs = 0;
+      }
+      if (aux_in && lane == 0) {
+        ptx::bulk_wait_read<0>();                 // the previous tile's stores have left the buffers
+        for (int sl = 0; sl < n_slabs && sl < NB; ++sl) {
+          ptx::mbar_expect_tx(aux_bar(q, sl), kStageBufBytes);
+          ptx::tma_load_4d(my_stage0 + (uint32_t)sl * kStageBufBytes, &tma_aux, aux_bar(q, sl), n0 + sl * 64, m0 + q * 32, 0, 0);
+        }
+      }
       ptx::mbar_wait(tfull_bar(as), aphase);
       ptx::tc_fence_after();
       if (prof && warp == kEpiWarp0 && lane == 0) { if (t == (int)blockIdx.x) prof_stamp(prof, 8); prof_stamp(prof, 9); }
@@ -394,30 +429,59 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       } else if (FAST || g.tma_store) {
         // ---- coalesced path: registers -> 128B-swizzled smem slab (32 rows x 64 cols) -> TMA store ------------------
 #pragma unroll 1
-        for (int slab = 0; slab < ((dbg & 4) ? 0 : BN / 64); ++slab) {
+        for (int slab = 0; slab < n_slabs; ++slab) {
           const int ns = n0 + slab * 64;
-          if (ns >= g.N) break;
           uint32_t dbuf, abuf = 0;
           // epilogue trace (tools/gemm_harness trace): first tile of CTA 0, first epilogue warp, slabs 0..1
           const bool etr = prof && blockIdx.x == 0 && t == 0 && warp == kEpiWarp0 && lane == 0 && slab < 2;
           long long* et = etr ? prof + 148 * 16 + 128 + slab * 8 : nullptr;
           if (etr) et[0] = clock64();
-          if (gelu_save || aux_in) { dbuf = my_stage0; abuf = my_stage0 + kStageBufBytes; if (lane == 0) ptx::bulk_wait_read<0>(); }
-          else { dbuf = my_stage0 + sbuf_toggle * kStageBufBytes; sbuf_toggle ^= 1u; if (lane == 0) ptx::bulk_wait_read<1>(); }
-          __syncwarp();
-          if (etr) et[1] = clock64();
           if (aux_in) {
-            // residual / pre-activation tile (32 rows x 64 cols) by TMA into the second staging buffer: coalesced 128-byte
-            // rows instead of one 16-byte global load per thread per row
-            if (lane == 0) {
-              ptx::mbar_expect_tx(aux_bar(q), kStageBufBytes);
-              ptx::tma_load_4d(abuf, &tma_aux, aux_bar(q), ns, m0 + q * 32, 0, 0);
+            const int bi = slab % NB;
+            dbuf = abuf = my_stage0 + (uint32_t)bi * kStageBufBytes;
+            if (etr) et[1] = clock64();
+            ptx::mbar_wait(aux_bar(q, bi), (aux_phase >> bi) & 1u);
+            aux_phase ^= 1u << bi;
+          } else if (gelu_save) {
+            // (output, pre-activation) pairs; one bulk group per slab holds both stores
+            constexpr int kPairs = NB / 2;
+            dbuf = my_stage0 + sbuf_toggle * 2u * kStageBufBytes;
+            abuf = dbuf + kStageBufBytes;
+            if (++sbuf_toggle == (uint32_t)kPairs) sbuf_toggle = 0;
+            if (lane == 0) ptx::bulk_wait_read<kPairs - 1>();
+            __syncwarp();
+            if (etr) et[1] = clock64();
+          } else {
+            dbuf = my_stage0 + sbuf_toggle * kStageBufBytes;
+            if (++sbuf_toggle == (uint32_t)NB) sbuf_toggle = 0;
+            if (lane == 0) ptx::bulk_wait_read<NB - 1>();
+            __syncwarp();
+            if (etr) et[1] = clock64();
+          }
+          // bias of the slab's 64 columns: 8 x 16 B at the same address in every lane (one broadcast transaction each), issued
+          // BEFORE the accumulator loads so their latency hides under them.  Columns past N are clipped by the TMA store,
+          // so the address is only clamped; no bias = add zeros.  (The previous form — a guarded 4 x 32-bit load per 8
+          // columns, then a branch per operand source — serialised eight load latencies per slab: profiles/r2_gemm_epilogue.md)
+          uint4 braw[8];
+#pragma unroll
+          for (int j8 = 0; j8 < 8; ++j8) braw[j8] = make_uint4(0u, 0u, 0u, 0u);
+          if (g.bias) {
+#pragma unroll
+            for (int j8 = 0; j8 < 8; ++j8) {
+              int nc = ns + j8 * 8;
+              nc = nc > g.N - 8 ? g.N - 8 : nc;
+              braw[j8] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.bias) + nc));
             }
-            ptx::mbar_wait(aux_bar(q), aux_phase);
-            aux_phase ^= 1u;
           }
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
+            // this thread's 4 x 16 B of the residual / pre-activation slab (same swizzled chunks the result goes back to)
+            uint4 ax[4];
+            if (aux_in) {
+#pragma unroll
+              for (int j8 = 0; j8 < 4; ++j8)
+                ax[j8] = ptx::ld_shared_16<uint4>(abuf + (uint32_t)(((half * 4 + j8) ^ (lane & 7)) * 16) + (uint32_t)lane * 128u);
+            }
             uint32_t raw[32];
             ld_acc(slab * 64 + half * 32, raw);
             if (etr) et[2 + half * 2] = clock64();
@@ -428,9 +492,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
 #pragma unroll
             for (int j8 = 0; j8 < 4; ++j8) {
               const int nc = nb + j8 * 8;
-              const bool col_ok = nc + 8 <= g.N;       // N % 8 == 0 on this path
-              if (g.bias && col_ok) {
-                float bf[8]; unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(g.bias) + nc), bf);
+              {
+                float bf[8]; unpack8(*reinterpret_cast<const bf16x8*>(&braw[half * 4 + j8]), bf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += bf[j];
               }
@@ -443,10 +506,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
                 for (int j = 0; j < 8; ++j) v[j8 * 8 + j] = gelu_tanh(af[j]);
               } else if (epi != EPI_NONE) {
                 float af[8];
+                if (aux_in) {
+                  unpack8(*reinterpret_cast<const bf16x8*>(&ax[j8]), af);                  // OOB rows/cols were zero-filled
+                } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) af[j] = 0.f;
-                if (aux_in) unpack8(ptx::ld_shared_16<bf16x8>(abuf + chunk), af);     // OOB rows/cols were zero-filled
-                else if (row_ok && col_ok) unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(g.aux) + (long long)m * g.ld_aux + nc), af);
+                  for (int j = 0; j < 8; ++j) af[j] = 0.f;
+                  if (row_ok && nc + 8 <= g.N) unpack8(ld8(reinterpret_cast<const __nv_bfloat16*>(g.aux) + (long long)m * g.ld_aux + nc), af);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
                   v[j8 * 8 + j] = epi == EPI_GELU_BWD ? v[j8 * 8 + j] * gelu_tanh_grad(af[j]) : v[j8 * 8 + j] + af[j];
@@ -462,6 +528,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             ptx::tma_store_4d(&tma_d, dbuf, ns, m0 + q * 32, b2, b1);
             if (gelu_save) ptx::tma_store_4d(&tma_aux, abuf, ns, m0 + q * 32, 0, 0);
             ptx::bulk_commit();
+          }
+          if (aux_in && slab + NB < n_slabs && lane == 0) {
+            // more slabs than buffers (BN = 256, or the runtime-epilogue kernels): recycle this buffer for slab + NB
+            ptx::bulk_wait_read<0>();
+            ptx::mbar_expect_tx(aux_bar(q, slab % NB), kStageBufBytes);
+            ptx::tma_load_4d(dbuf, &tma_aux, aux_bar(q, slab % NB), ns + NB * 64, m0 + q * 32, 0, 0);
           }
           if (etr) et[7] = clock64();
         }
@@ -782,6 +854,10 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
   g.epi = p.aux ? p.epi : EPI_NONE; g.accumulate = p.accumulate ? 1 : 0; g.alpha = p.alpha;
   g.M = p.M; g.N = p.N; g.K = p.K; g.batch = p.batch; g.nb2 = nb2;
   g.a_mn = p.a.mn_major; g.b_mn = p.b.mn_major; g.tri = p.tri;
+  g.pf = nullptr; g.pf_bytes = 0;
+  if (p.prefetch && p.prefetch_bytes >= 16 && (reinterpret_cast<uintptr_t>(p.prefetch) & 15) == 0) {
+    g.pf = reinterpret_cast<const char*>(p.prefetch); g.pf_bytes = p.prefetch_bytes & ~15LL;
+  }
   if (g_dbg < 0) g_dbg = getenv("TDS_GEMM_DBG") ? atoi(getenv("TDS_GEMM_DBG")) : 0;
   g.dbg = g_dbg;
   g.prof = g_prof;
@@ -801,7 +877,8 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
       fprintf(stderr, "[tds] gemm: reduce_out needs bf16 operands and a 16-byte aligned fp32 [M,N] destination\n");
       abort();
     }
-  } else if (!no_tma_store && p.d_dtype == kBF16 && !p.accumulate && aligned && !g.io_f32) {
+  } else if (!no_tma_store && p.d_dtype == kBF16 && !p.accumulate && aligned && !g.io_f32 && p.N >= 8 &&
+             (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0) {
     GemmOperand od{p.d, p.ldd, p.d_batch_stride, p.d_batch_stride2, false};
     bool ok = make_map(&td, od, p.M, p.N, nb1, nb2, 32);
     if (ok && g.epi != EPI_NONE) {
@@ -836,7 +913,7 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
     TDS_BY_BN(false, true, -1, false);
   } else if (f32) {
     TDS_BY_BN(true, false, -1, false);
-  } else if (g.tma_store) {
+  } else if (g.tma_store && (g.aux_tma || g.epi == EPI_NONE || g.epi == EPI_GELU_SAVE)) {
     // the bf16 training step lives here: epilogue functor and store path fixed at compile time
     if (g.epi == EPI_NONE) TDS_BY_BN(false, false, EPI_NONE, true);
     else if (g.epi == EPI_GELU_SAVE) TDS_BY_BN(false, false, EPI_GELU_SAVE, true);

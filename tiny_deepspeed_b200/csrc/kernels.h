@@ -32,6 +32,9 @@ struct GemmParams {
   int cluster_m;          // requested cluster size along M for B-tile multicast (0 = default, 1 = off)
   int tri;                // causal structure: 0 none, 1 skip tiles above the diagonal (S, dP),
                           // 2 K-range ends at the tile's last row (P.V, dS.K), 3 K-range starts at the tile's first row (P^T.dY, dS^T.Q)
+  // L2 prefetch hint: `prefetch_bytes` bytes at `prefetch` (the weight / saved activation the NEXT kernel will stream) are
+  // requested into L2 by this kernel's otherwise idle epilogue warps while its own main loop runs.  nullptr = none.
+  const void* prefetch = nullptr;  int64_t prefetch_bytes = 0;
 };
 void gemm_bf16(const GemmParams& p, cudaStream_t stream);
 // EXPERIMENTAL CTA-pair (cta_group::2) variant, gemm2_sm100.cu: returns false without launching when the problem is outside

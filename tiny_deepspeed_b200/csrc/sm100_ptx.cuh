@@ -118,6 +118,10 @@ TDS_PTX void tma_reduce_add_2d(const CUtensorMap* m, uint32_t src_smem, int c0, 
                : "memory");
 }
 TDS_PTX void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// ask L2 to fetch `bytes` (multiple of 16) at a 16-byte aligned global address; no destination, no completion to wait for
+TDS_PTX void prefetch_l2_bulk(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
+}
 template <int N> TDS_PTX void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 template <typename T16> TDS_PTX void st_shared_16(uint32_t addr, const T16& v) {
   static_assert(sizeof(T16) == 16, "16-byte payload");

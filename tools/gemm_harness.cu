@@ -124,6 +124,33 @@ static float time_graph(const tds::GemmParams& p, int pair, int iters = 30) {
   CK(cudaGraphExecDestroy(exec)); CK(cudaGraphDestroy(graph)); CK(cudaStreamDestroy(st));
   return ms * 1e3f / (5 * iters);
 }
+// The training step never finds a weight in L2 (250 MB of them per pass): launch i uses B buffer i % nbuf (pool > L2), A stays hot
+// like the activation a previous kernel just wrote.  prefetch: launch i also asks for launch i+1's B through the kernel's L2 hint.
+static float time_graph_rot(const tds::GemmParams& p, const std::vector<__nv_bfloat16*>& pool, size_t bbytes, bool prefetch, int iters = 60) {
+  cudaStream_t st;
+  CK(cudaStreamCreate(&st));
+  cudaGraph_t graph; cudaGraphExec_t exec;
+  CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeGlobal));
+  for (int i = 0; i < iters; ++i) {
+    tds::GemmParams q = p;
+    q.b.ptr = pool[i % pool.size()];
+    if (prefetch) { q.prefetch = pool[(i + 1) % pool.size()]; q.prefetch_bytes = (int64_t)bbytes; }
+    tds::gemm_bf16(q, st);
+  }
+  CK(cudaStreamEndCapture(st, &graph));
+  CK(cudaGraphInstantiate(&exec, graph, 0));
+  for (int i = 0; i < 3; ++i) CK(cudaGraphLaunch(exec, st));
+  cudaEvent_t e0, e1;
+  CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+  CK(cudaEventRecord(e0, st));
+  for (int i = 0; i < 5; ++i) CK(cudaGraphLaunch(exec, st));
+  CK(cudaEventRecord(e1, st));
+  CK(cudaEventSynchronize(e1));
+  float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
+  CK(cudaEventDestroy(e0)); CK(cudaEventDestroy(e1));
+  CK(cudaGraphExecDestroy(exec)); CK(cudaGraphDestroy(graph)); CK(cudaStreamDestroy(st));
+  return ms * 1e3f / (5 * iters);
+}
 static float time_cold(const tds::GemmParams& p, int pair, int iters = 9) {
   std::vector<float> v;
   cudaEvent_t e0, e1;
@@ -151,13 +178,15 @@ static double check(const Shape& s, const Bufs& bf, const tds::GemmParams& p, in
 }
 
 int main(int argc, char** argv) {
-  bool do_check = false, sweep = false, dbg = false, trace = false, nobias = true;
+  bool do_check = false, sweep = false, dbg = false, trace = false, nobias = true, rot = false, epi_mode = false;
   std::string only;
   for (int i = 1; i < argc; ++i) {
     if (!strcmp(argv[i], "check")) do_check = true;
     else if (!strcmp(argv[i], "sweep")) sweep = true;
     else if (!strcmp(argv[i], "dbg")) dbg = true;
     else if (!strcmp(argv[i], "trace")) trace = true;
+    else if (!strcmp(argv[i], "rot")) rot = true;
+    else if (!strcmp(argv[i], "epi")) epi_mode = true;
     else if (!strcmp(argv[i], "bias")) nobias = false;
     else only = argv[i];
   }
@@ -179,6 +208,72 @@ int main(int argc, char** argv) {
       dim3 g((s.N + 127) / 128, s.M);
       ref_gemm<<<g, 128>>>(bf.a, bf.b, nobias ? nullptr : bf.bias, bf.ref, s.M, s.N, s.K, s.a_mn, s.b_mn);
       CK(cudaDeviceSynchronize());
+    }
+    if (epi_mode && trace) {
+      // per-phase cycle medians of the epilogue variants (prof build only)
+      if (big) continue;
+      __nv_bfloat16* aux; CK(cudaMalloc(&aux, (size_t)s.M * s.N * 2)); CK(cudaMemset(aux, 0, (size_t)s.M * s.N * 2));
+      static long long* prof = nullptr;
+      if (!prof) CK(cudaMalloc(&prof, (148 * 16 + 256) * 8));
+      printf("%-16s %6d %6d %6d %d%d\n", s.name, s.M, s.N, s.K, s.a_mn, s.b_mn);
+      const char* vn[] = {"plain", "bias", "bias+residual", "bias+GELU-save", "GELU-bwd"};
+      for (int variant = 0; variant < 5; ++variant) {
+        tds::GemmParams p = make_params(s, bf, -1, variant >= 1 && variant <= 3);
+        if (variant >= 2) { p.aux = aux; p.ld_aux = s.N; p.epi = variant == 2 ? 3 : (variant == 3 ? 1 : 2); }
+        for (int i = 0; i < 10; ++i) run(p, 0);
+        CK(cudaMemset(prof, 0, (148 * 16 + 256) * 8));
+        tds::gemm_set_prof(prof);
+        run(p, 0);
+        tds::gemm_set_prof(nullptr);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> h(148 * 16 + 256);
+        CK(cudaMemcpy(h.data(), prof, h.size() * 8, cudaMemcpyDeviceToHost));
+        long long t0 = h[0], t1 = h[14];
+        std::vector<long long> main_, epi, wr, tail, tot;
+        for (int b = 0; b < 148; ++b) if (h[b * 16 + 1]) {
+          t0 = std::min(t0, h[b * 16]); t1 = std::max(t1, h[b * 16 + 14]);
+          main_.push_back(h[b * 16 + 9] - h[b * 16 + 2]); epi.push_back(h[b * 16 + 10] - h[b * 16 + 9]);
+          wr.push_back(h[b * 16 + 11] - h[b * 16 + 10]); tail.push_back(h[b * 16 + 13] - h[b * 16 + 11]); tot.push_back(h[b * 16 + 14] - h[b * 16 + 0]);
+        }
+        auto med = [](std::vector<long long>& v) { std::sort(v.begin(), v.end()); return v.empty() ? 0LL : v[v.size() / 2]; };
+        printf("  %-16s wall %6lld ns | CTAs %3zu: until accumulator %6lld cyc, epilogue body %6lld, store-read wait %5lld, exit sync %5lld, CTA lifetime %6lld ns | slab0:",
+               vn[variant], t1 - t0, tot.size(), med(main_), med(epi), med(wr), med(tail), med(tot));
+        const long long* tr = &h[148 * 16 + 128];
+        if (tr[0]) for (int i = 1; i <= 7; ++i) printf(" %5lld", tr[i] - tr[0]);
+        printf("\n");
+      }
+      CK(cudaFree(aux));
+      continue;
+    }
+    if (epi_mode) {
+      if (big) continue;
+      __nv_bfloat16* aux; CK(cudaMalloc(&aux, (size_t)s.M * s.N * 2)); CK(cudaMemset(aux, 0, (size_t)s.M * s.N * 2));
+      printf("%-16s %6d %6d %6d %d%d  | in-graph us (B hot):", s.name, s.M, s.N, s.K, s.a_mn, s.b_mn);
+      for (int cfg : {-1, 0, 1, 3}) {
+        if (cfg == 3 && s.N % 192) continue;
+        printf("  cfg %2d:", cfg);
+        for (int variant = 0; variant < 5; ++variant) {   // plain, +bias, +bias+residual, +bias+GELU save, GELU' (no bias)
+          tds::GemmParams p = make_params(s, bf, cfg, variant >= 1 && variant <= 3);
+          if (variant >= 2) { p.aux = aux; p.ld_aux = s.N; p.epi = variant == 2 ? 3 : (variant == 3 ? 1 : 2); }
+          printf(" %5.2f", time_graph(p, 0, 60));
+        }
+      }
+      printf("   (plain, bias, bias+residual, bias+GELU-save, GELU-bwd)\n");
+      CK(cudaFree(aux));
+      continue;
+    }
+    if (rot) {
+      if (big) continue;
+      const size_t bbytes = (size_t)s.N * s.K * 2;
+      size_t nbuf = ((size_t)400 << 20) / bbytes + 1; if (nbuf > 120) nbuf = 120;
+      std::vector<__nv_bfloat16*> pool(nbuf);
+      for (auto& q : pool) { CK(cudaMalloc(&q, bbytes)); CK(cudaMemcpy(q, bf.b, bbytes, cudaMemcpyDeviceToDevice)); }
+      tds::GemmParams p = make_params(s, bf, -1, !nobias);
+      const float hot = time_graph(p, 0, 60), cold = time_graph_rot(p, pool, bbytes, false), pf = time_graph_rot(p, pool, bbytes, true);
+      printf("%-16s %6d %6d %6d %d%d  | in-graph us: B hot %5.2f   B from HBM (pool of %zu) %5.2f   + L2 prefetch by the previous launch %5.2f\n",
+             s.name, s.M, s.N, s.K, s.a_mn, s.b_mn, hot, nbuf, cold, pf);
+      for (auto q : pool) CK(cudaFree(q));
+      continue;
     }
     printf("%-16s %6d %6d %6d %d%d  |", s.name, s.M, s.N, s.K, s.a_mn, s.b_mn);
     for (int v = 0; v < nvar; ++v) {
