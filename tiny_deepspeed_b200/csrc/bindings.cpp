@@ -62,6 +62,15 @@ void gemm_set_prof_t(const c10::optional<Tensor>& buf) {
   gemm_set_prof(buf ? reinterpret_cast<long long*>(buf->data_ptr()) : nullptr);
 }
 
+// L2 prefetch hint consumed by the next gemm() call (ops.prefetch_next): pointer + bytes of a resident tensor
+static const void* g_prefetch_ptr = nullptr;
+static int64_t g_prefetch_bytes = 0;
+void gemm_set_prefetch(const Tensor& t) {
+  if (!t.defined() || !t.is_cuda() || t.numel() == 0 || !t.is_contiguous()) { g_prefetch_ptr = nullptr; g_prefetch_bytes = 0; return; }
+  g_prefetch_ptr = t.data_ptr();
+  g_prefetch_bytes = (int64_t)t.numel() * (int64_t)t.element_size();
+}
+
 void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, const c10::optional<Tensor>& bias,
           const c10::optional<Tensor>& aux, int64_t epi, bool accumulate, double alpha, int64_t config, int64_t tri,
           int64_t cluster, bool reduce_out) {
@@ -107,6 +116,10 @@ void gemm(const Tensor& a, const Tensor& b, Tensor& d, bool a_mn, bool b_mn, con
   if (g_use_pair && gemm2_bf16(p, cur_stream())) {
     check_launch("gemm2");
     return;
+  }
+  if (g_prefetch_ptr) {   // one-shot L2 hint set by gemm_set_prefetch(): the operand the NEXT kernel will stream
+    p.prefetch = g_prefetch_ptr; p.prefetch_bytes = g_prefetch_bytes;
+    g_prefetch_ptr = nullptr; g_prefetch_bytes = 0;
   }
   gemm_bf16(p, cur_stream());
   check_launch("gemm");
@@ -383,6 +396,7 @@ void bind_comm(pybind11::module_& m);  // comm_bindings.cpp
 PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "tiny_deepspeed_b200 sm_100a kernels";
   m.def("gemm", &gemm, "persistent tcgen05 GEMM");
+  m.def("gemm_set_prefetch", &gemm_set_prefetch, "one-shot L2 prefetch hint for the next gemm launch");
   m.def("gemm_num_configs", &gemm_num_configs);
   m.def("set_gemm_pair", &set_gemm_pair, "route eligible GEMMs through the cta_group::2 kernel (0/1)");
   m.def("gemm_set_prof", &gemm_set_prof_t, "install / clear the per-CTA phase timestamp buffer (tools/gemm_timeline.py)");

@@ -21,9 +21,10 @@ TDS_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); 
 TDS_DEVICE void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 inline bool pdl_enabled() {
-  // measured (profiles/r1_pdl.md): inside the CUDA graph the step is 4.87 ms without and 4.98 ms with PDL edges, so
-  // the attribute is opt-in (TDS_PDL=1); the griddepcontrol instructions are no-ops without it
-  static const bool on = getenv("TDS_PDL") && atoi(getenv("TDS_PDL")) != 0;
+  // Round 1 (4.87 ms step, kernels 10-30 us): 4.98 ms with PDL edges, so it was opt-in.  Round 2 (3.3 ms step, GEMMs of
+  // 6-10 us whose barrier init / TMEM alloc / descriptor prefetch are ~1 us of prologue): 3.30 -> 3.24 ms with the edges
+  // (profiles/r2_step_sweeps.md), so it is ON unless TDS_PDL=0; the griddepcontrol instructions are no-ops without it
+  static const bool on = !(getenv("TDS_PDL") && atoi(getenv("TDS_PDL")) == 0);
   return on;
 }
 

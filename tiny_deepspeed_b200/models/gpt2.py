@@ -20,7 +20,7 @@ import torch.nn as tnn
 from torch.nn import functional as F
 
 from .. import nn as tds
-from ..nn.modules import fused_mlp
+from ..nn.modules import fused_mlp, link_prefetch_chain
 
 __all__ = ["GPTConfig", "GPT2Model", "standard_attention", "flash_attention", "CausalSelfAttention",
            "MLP", "Block", "PRESETS", "gpt2_config"]
@@ -128,6 +128,11 @@ class GPT2Model(tnn.Module):
         ))
         self.lm_head = tds.Linear(config.n_embd, config.vocab_size, bias=False)
         self._pos_cache = {}
+        # L2 prefetch chain: every GEMM asks L2 for the weight of the GEMM that follows it in the pass (nn/modules.py)
+        chain = []
+        for blk in self.transformer.h:
+            chain += [blk.attn.c_attn, blk.attn.c_proj, blk.mlp.c_fc, blk.mlp.c_proj]
+        link_prefetch_chain(chain + [self.lm_head])
 
     def _positions(self, T, device):
         key = (T, str(device))

@@ -77,6 +77,22 @@ def _linear_backward(pol, weight, shape, dy, x, tuner, dx_fn):
     return dx
 
 
+def _hint(module, attr):
+    """L2 prefetch hint for the GEMM about to be launched: the weight of the Linear whose GEMM comes next in this pass
+    (``link_prefetch_chain``).  Stored as a module reference (not a Parameter) so nothing is registered twice."""
+    nxt = module.__dict__.get(attr)
+    if nxt is not None:
+        ops.prefetch_next(nxt.weight.data)
+
+
+def link_prefetch_chain(linears):
+    """``linears``: the model's Linear layers in forward execution order.  Layer i's forward GEMM will prefetch layer i+1's
+    weight into L2, its dX GEMM layer i-1's (ops.prefetch_next)."""
+    for a, b in zip(linears, linears[1:]):
+        object.__setattr__(a, "_pf_fwd", b)
+        object.__setattr__(b, "_pf_bwd", a)
+
+
 # ----------------------------------------------------------------------------------------
 # Linear
 # ----------------------------------------------------------------------------------------
@@ -87,6 +103,7 @@ class _LinearFn(torch.autograd.Function):
     def forward(ctx, x, weight, bias, module, residual):
         pol = policy_of(module)
         w = pol.acquire(weight)
+        _hint(module, "_pf_fwd")
         y = ops.linear_forward(x, w, bias, getattr(module, "runtime_tuner", None), residual=residual)
         pol.release(weight, w)
         ctx.module = module
@@ -110,6 +127,7 @@ class _LinearFn(torch.autograd.Function):
             if not ctx.needs_input_grad[0]:
                 return None
             w = pol.acquire(weight, backward=True)
+            _hint(module, "_pf_bwd")
             d = ops.linear_input_grad(dy, w, tuner)
             pol.release(weight, w)
             return d
@@ -140,9 +158,11 @@ class _MLPFn(torch.autograd.Function):
         pf, pp = policy_of(fc), policy_of(proj)
         pre = torch.empty(*x.shape[:-1], fc.out_features, device=x.device, dtype=x.dtype)
         w = pf.acquire(fc.weight)
+        _hint(fc, "_pf_fwd")
         act = ops.linear_forward(x, w, fc.bias, gelu_aux=pre)
         pf.release(fc.weight, w)
         w = pp.acquire(proj.weight)
+        _hint(proj, "_pf_fwd")
         y = ops.linear_forward(act, w, proj.bias, residual=residual)
         pp.release(proj.weight, w)
         ctx.fc, ctx.proj = fc, proj
@@ -162,6 +182,7 @@ class _MLPFn(torch.autograd.Function):
 
         def dpre_fn():
             w = pp.acquire(proj.weight, backward=True)
+            _hint(proj, "_pf_bwd")
             d = ops.linear_input_grad(dy, w, gelu_aux=pre)       # GELU' folded into the dX epilogue
             pp.release(proj.weight, w)
             return d
@@ -174,6 +195,7 @@ class _MLPFn(torch.autograd.Function):
             if not ctx.needs_input_grad[0]:
                 return None
             w = pf.acquire(fc.weight, backward=True)
+            _hint(fc, "_pf_bwd")
             d = ops.linear_input_grad(dpre, w)
             pf.release(fc.weight, w)
             return d

@@ -98,6 +98,23 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+_L2_PREFETCH = os.environ.get("TDS_L2_PREFETCH", "1") != "0"
+_L2_PREFETCH_MAX = 16 << 20
+
+
+def prefetch_next(t):
+    """L2 hint: the next GEMM launch also asks L2 to fetch ``t`` (the weight the FOLLOWING kernel will stream from HBM) with its
+    idle epilogue warps while its own main loop runs (``cp.async.bulk.prefetch.L2``; csrc/gemm_sm100.cu).  At 1 x 1024 tokens
+    every weight of a pass comes from HBM (250 MB of them against 126 MB of L2) into a latency-bound single-wave GEMM;
+    measured per GEMM: profiles/r2_gemm_rot.log.  No-op on CPU, for empty (non-resident ZeRO-3) or very large tensors."""
+    if not _L2_PREFETCH or t is None or not t.is_cuda or is_forced_torch():
+        return
+    nbytes = t.numel() * t.element_size()
+    if nbytes < 16 or nbytes > _L2_PREFETCH_MAX or not t.is_contiguous():
+        return
+    ext().gemm_set_prefetch(t)
+
+
 def _gemm_cuda(a, b, a_mn, b_mn, out, out_dtype, bias, aux, epi, accumulate, alpha, config, tri=0, cluster=0, reduce_out=False):
     if getattr(b, "_tds_remote", False):
         # B aliases a peer GPU's memory (ZeRO-3 direct-fetch mode).  TMA *multicast* sourced from peer-mapped memory
