@@ -5,9 +5,12 @@
 //   warp 1    MMA issuer:   S_j = Q K_j^T  (UMMA 128x128x16, 4 k-steps)  -> TMEM S[j&1]
 //                           PV_j = P_j V_j (UMMA 128x64x16, 8 k-steps, V consumed MN-major) -> TMEM PV[j&1]
 //             S_{j+1} is issued before PV_j so the tensor core works underneath the softmax of block j
-//   warps 2-5 softmax / correction / epilogue: thread == query row (tcgen05.ld 32x32b), online softmax in the
-//             log2 domain, P_j written as bf16 into 128B-swizzled smem (the A operand of PV_j), running output
-//             kept in registers (O = O * alpha + PV_j), final O / l through swizzled smem + TMA store, LSE to HBM
+//   warps 2-9 softmax / correction / epilogue: TWO threads per query row (warps w and w + 4 share a TMEM lane quadrant; each
+//             takes 64 of the block's 128 score columns and 32 of the 64 output columns), S read from TMEM once, row maximum
+//             agreed through smem + a 64-thread named barrier, online softmax in the log2 domain, P_j written as bf16 into
+//             128B-swizzled smem (the A operand of PV_j), running output in registers (O = O * alpha + PV_j), final O / l
+//             through swizzled smem + TMA store, LSE to HBM.  (One thread per row was a single warp per scheduler running a
+//             ~3000-instruction dependent stream per key block: 17.8 us per launch at T = 1024; profiles/r2_timeline_small.md)
 // Only the diagonal block is masked; blocks above the diagonal are never touched.
 //
 // Replaces the reference's standard_attention (example/model.py:29-42: QK^T, mask, softmax, PV as four ATen ops
@@ -28,11 +31,11 @@ namespace {
 
 constexpr int FB = 128;          // query rows per CTA == keys per KV block
 constexpr int HS = 64;           // head size
-constexpr int kFThreads = 192;       // forward: producer, issuer, 4 softmax warps
-constexpr int kFBThreads = 224;      // backward: + a second MMA issuer (warp 6)
+constexpr int kFThreads = 320;       // forward: producer, issuer, 8 softmax warps (two per TMEM lane quadrant)
+constexpr int kFBThreads = 352;      // backward: producer, issuer A, 8 softmax warps, issuer B (warp 10)
 constexpr uint32_t kTileQK = FB * HS * 2;        // 16 KB: one [128 x 64] bf16 tile
 constexpr uint32_t kTileP = FB * FB * 2;         // 32 KB: P as two K-major 64-column slabs
-constexpr uint32_t kFwdSmem = kTileQK * 5 + kTileP * 2 + 1024 + 256;
+constexpr uint32_t kFwdSmem = kTileQK * 5 + kTileP * 2 + 1024 + 256 + 2048 /*row-max / row-sum exchange*/;
 
 struct FlashDev {
   int T, nh;
@@ -56,6 +59,7 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   auto bar = [&](int i) { return sBar + 8u * i; };
   const uint32_t tmem_slot = sBar + 8u * NBAR;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
+  float* xch = reinterpret_cast<float*>(smem_raw + (sBar + 256u - ptx::smem_u32(smem_raw)));   // [2 parities][2 halves][128 rows]
 
   // warp index through a shuffle: provably warp-uniform, so role branches are uniform and issue code can use elect.sync
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -69,9 +73,9 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     ptx::mbar_init(bar(Q_FULL), 1);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(bar(KV_FULL + s), 1);  ptx::mbar_init(bar(KV_EMPTY + s), 1);
-      ptx::mbar_init(bar(S_FULL + s), 1);   ptx::mbar_init(bar(S_FREE + s), 4);
-      ptx::mbar_init(bar(P_FULL + s), 4);   ptx::mbar_init(bar(P_FREE + s), 1);
-      ptx::mbar_init(bar(PV_FULL + s), 1);  ptx::mbar_init(bar(PV_FREE + s), 4);
+      ptx::mbar_init(bar(S_FULL + s), 1);   ptx::mbar_init(bar(S_FREE + s), 8);
+      ptx::mbar_init(bar(P_FULL + s), 8);   ptx::mbar_init(bar(P_FREE + s), 1);
+      ptx::mbar_init(bar(PV_FULL + s), 1);  ptx::mbar_init(bar(PV_FREE + s), 8);
     }
     ptx::fence_mbar_init();
   }
@@ -134,27 +138,26 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       __syncwarp();
     }
   } else {
-    const int q = warp & 3;
+    const int q = warp & 3;                        // TMEM lane quadrant of this warp
+    const int hf = (warp - 2) >> 2;                // which half of the score / output columns this thread owns
     const int row = q * 32 + lane;                 // row inside the 128-query block
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };   // the two warps of a quadrant
     float m = -1e30f, l = 0.f;
-    float o[HS];
+    float o[HS / 2];
 #pragma unroll
-    for (int i = 0; i < HS; ++i) o[i] = 0.f;
+    for (int i = 0; i < HS / 2; ++i) o[i] = 0.f;
     float alpha_prev = 1.f;
-    // O = O * alpha_j + P_j V_j   (alpha_j rescales everything accumulated BEFORE block j)
+    // O = O * alpha_j + P_j V_j   (alpha_j rescales everything accumulated BEFORE block j); this thread: 32 of the 64 columns
     auto o_update = [&](int jj, float a) {
       const int st2 = jj & 1; const uint32_t ph2 = (jj >> 1) & 1;
       ptx::mbar_wait(bar(PV_FULL + st2), ph2);
       ptx::tc_fence_after();
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(tPV + st2 * 64 + lane_sel + hf * 32, raw);
+      ptx::tmem_ld_wait();
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(tPV + st2 * 64 + lane_sel + c * 32, raw);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[c * 32 + i] = o[c * 32 + i] * a + __uint_as_float(raw[i]);
-      }
+      for (int i = 0; i < 32; ++i) o[i] = o[i] * a + __uint_as_float(raw[i]);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(bar(PV_FREE + st2));
@@ -164,51 +167,62 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       const bool diag = (j == qb);
       ptx::mbar_wait(bar(S_FULL + st), ph);
       ptx::tc_fence_after();
-      const uint32_t t_s = tS + st * 128 + lane_sel;
-      // pass 1: row maximum (TMEM reads are cheap; two passes keep only 32 values live)
+      // this thread's 64 scores, read ONCE; the accumulator stage goes back to the issuer right away
+      const uint32_t t_s = tS + st * 128 + lane_sel + hf * 64;
+      uint32_t raw[64];
+      ptx::tmem_ld_32x32(t_s, &raw[0]);
+      ptx::tmem_ld_32x32(t_s + 32, &raw[32]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(S_FREE + st));
+      const int lim = row - hf * 64;               // diagonal block: column i of this half is visible iff i <= lim
       float mx = -1e30f;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(t_s + c * 32, raw);
-        ptx::tmem_ld_wait();
+      if (diag) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float v = __uint_as_float(raw[i]);
-          if (!diag || c * 32 + i <= row) mx = fmaxf(mx, v);
-        }
+        for (int i = 0; i < 64; ++i) if (i <= lim) mx = fmaxf(mx, __uint_as_float(raw[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(raw[i]));
       }
-      const float m_new = fmaxf(m, mx);
+      // agree on the row maximum with the thread that owns the other 64 columns (double-buffered by block parity)
+      float* xm = xch + (j & 1) * 256;
+      xm[hf * 128 + row] = mx;
+      pair_sync();
+      const float m_new = fmaxf(m, fmaxf(mx, xm[(hf ^ 1) * 128 + row]));
       const float alpha = exp2f((m - m_new) * g.cs);
       const float mcs = m_new * g.cs;
-      // pass 2: probabilities -> bf16 -> swizzled smem (A operand of P V)
+      // probabilities -> bf16 -> this half's 64-column K-major slab of P (A operand of P V)
       ptx::mbar_wait(bar(P_FREE + st), ph ^ 1u);
       float rs = 0.f;
-      const uint32_t pbuf = sP + st * kTileP;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(t_s + c * 32, raw);
-        ptx::tmem_ld_wait();
-        float p[32];
+      const uint32_t slab = sP + st * kTileP + (uint32_t)hf * (FB * 128) + (uint32_t)row * 128u;
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const float e = exp2f(__uint_as_float(raw[i]) * g.cs - mcs);
-          p[i] = (!diag || c * 32 + i <= row) ? e : 0.f;
-          rs += p[i];
+      for (int c = 0; c < 2; ++c) {
+        float p[32];
+        if (diag) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float e = exp2f(__uint_as_float(raw[c * 32 + i]) * g.cs - mcs);
+            p[i] = (c * 32 + i <= lim) ? e : 0.f;
+            rs += p[i];
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            p[i] = exp2f(__uint_as_float(raw[c * 32 + i]) * g.cs - mcs);
+            rs += p[i];
+          }
         }
-        const uint32_t slab = pbuf + (uint32_t)(c >> 1) * (FB * 128) + (uint32_t)row * 128u;
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
-          const uint32_t idx = (uint32_t)((c & 1) * 4 + j8);
+          const uint32_t idx = (uint32_t)(c * 4 + j8);
           ptx::st_shared_16(slab + ((idx ^ (uint32_t)(row & 7)) << 4), pack8(&p[j8 * 8]));
         }
       }
-      ptx::tc_fence_before();
       ptx::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(bar(S_FREE + st)); ptx::mbar_arrive(bar(P_FULL + st)); }
-      l = l * alpha + rs;
+      if (lane == 0) ptx::mbar_arrive(bar(P_FULL + st));
+      l = l * alpha + rs;                          // partial row sum over this thread's columns (same alpha in both threads)
       m = m_new;
       // O update of the PREVIOUS block (software pipelining: P_{j-1} V_{j-1} ran on the tensor core while this
       // thread was busy with the softmax of block j), then remember this block's rescale factor
@@ -216,25 +230,32 @@ flash_fwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       alpha_prev = alpha;
     }
     o_update(n_kv - 1, alpha_prev);
+    // row sum = the two partial sums
+    float* xl = xch + (n_kv & 1) * 256;
+    xl[hf * 128 + row] = l;
+    pair_sync();
+    l += xl[(hf ^ 1) * 128 + row];
     // epilogue: O / l -> bf16 -> swizzled staging (sP[0] is free: every P V has completed) -> TMA store
     const float inv = 1.f / l;
     const uint32_t stg = sP + (uint32_t)q * 4096u + (uint32_t)lane * 128u;
 #pragma unroll
-    for (int j8 = 0; j8 < 8; ++j8) {
+    for (int j8 = 0; j8 < 4; ++j8) {
       float t[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) t[i] = o[j8 * 8 + i] * inv;
-      ptx::st_shared_16(stg + (((uint32_t)j8 ^ (uint32_t)(lane & 7)) << 4), pack8(t));
+      ptx::st_shared_16(stg + (((uint32_t)(hf * 4 + j8) ^ (uint32_t)(lane & 7)) << 4), pack8(t));
     }
     ptx::fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      ptx::tma_store_4d(&tma_o, sP + (uint32_t)q * 4096u, 0, qb * FB + q * 32, h, b);
-      ptx::bulk_commit();
+    pair_sync();                                   // both halves of the 32 x 64 staging slab are written
+    if (hf == 0) {
+      if (lane == 0) {
+        ptx::tma_store_4d(&tma_o, sP + (uint32_t)q * 4096u, 0, qb * FB + q * 32, h, b);
+        ptx::bulk_commit();
+      }
+      g.lse[((size_t)b * g.nh + h) * g.T + qb * FB + row] = m * g.cs + log2f(l);
+      if (lane == 0) ptx::bulk_wait_read<0>();
+      __syncwarp();
     }
-    g.lse[((size_t)b * g.nh + h) * g.T + qb * FB + row] = m * g.cs + log2f(l);
-    if (lane == 0) ptx::bulk_wait_read<0>();
-    __syncwarp();
   }
 
   ptx::tc_fence_before();
@@ -273,7 +294,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   const uint32_t sDO = sQ + 2 * kTileQK;            // 2 stages
   const uint32_t sP = sDO + 2 * kTileQK;
   const uint32_t sDS = sP + kTileP;
-  const uint32_t sStg = sDS + kTileP;               // 4 warps x 2 x 4 KB (fp32 dQ halves)
+  const uint32_t sStg = sDS + kTileP;               // 8 warps x 4 KB (fp32 dQ quarter / bf16 dV or dK slab)
   const uint32_t sBar = sStg + 32768;
   enum { KV_FULL = 0, QDO_FULL = 1, QDO_EMPTY = 3, SDP_FULL = 5, SDP_FREE = 6, PDS_FULL = 7, PDS_FREE = 8, DQ_FULL = 9, DQ_FREE = 10, DKV_DONE = 11, NBAR = 12 };
   auto bar = [&](int i) { return sBar + 8u * i; };
@@ -291,9 +312,9 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     ptx::mbar_init(bar(KV_FULL), 1);
     // Q / dO stages and the P / dS tiles are read by BOTH issuers: two commits release them
     for (int s = 0; s < 2; ++s) { ptx::mbar_init(bar(QDO_FULL + s), 1); ptx::mbar_init(bar(QDO_EMPTY + s), 2); }
-    ptx::mbar_init(bar(SDP_FULL), 1); ptx::mbar_init(bar(SDP_FREE), 4);
-    ptx::mbar_init(bar(PDS_FULL), 4); ptx::mbar_init(bar(PDS_FREE), 2);
-    ptx::mbar_init(bar(DQ_FULL), 1);  ptx::mbar_init(bar(DQ_FREE), 4);
+    ptx::mbar_init(bar(SDP_FULL), 1); ptx::mbar_init(bar(SDP_FREE), 8);
+    ptx::mbar_init(bar(PDS_FULL), 8); ptx::mbar_init(bar(PDS_FREE), 2);
+    ptx::mbar_init(bar(DQ_FULL), 1);  ptx::mbar_init(bar(DQ_FREE), 8);
     ptx::mbar_init(bar(DKV_DONE), 1);
     ptx::fence_mbar_init();
   }
@@ -319,30 +340,37 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===== issuer A: S = Q K^T, dP = dO V^T (8 MMAs), then dQ = dS K (8 MMAs) =====
+    // ===== issuer A: S = Q K^T, dP = dO V^T (8 MMAs) and dQ = dS K (8 MMAs) =====
     // One thread issues a tcgen05.mma only every ~80-100 cycles (tools/mma_probe.cu): the 32 MMAs of an (i, j) step cost one
     // issuer ~2900 cycles against ~1300 cycles of tensor-pipe work, so the step is split between two issuing warps.
+    // Order: as soon as P_i / dS_i exist, S / dP of step i+1 go FIRST (the softmax warps wait for nothing else), dQ_i second
+    // (its read-out by the softmax warps is deferred by one step, off the critical path).
     ptx::mbar_wait_conv(bar(KV_FULL), 0);
-    for (int it = 0; it < n_it; ++it) {
-      const int st = it & 1; const uint32_t ph2 = (it >> 1) & 1, ph = it & 1;
+    auto issue_sdp = [&](int k) {
+      const int st = k & 1; const uint32_t ph2 = (k >> 1) & 1, ph = k & 1;
       const uint32_t q_s = sQ + st * kTileQK, do_s = sDO + st * kTileQK;
       ptx::mbar_wait_conv(bar(QDO_FULL + st), ph2);
-      ptx::mbar_wait_conv(bar(SDP_FREE), ph ^ 1u);
+      ptx::mbar_wait_conv(bar(SDP_FREE), ph ^ 1u);       // S / dP of step k-1 have been read out of TMEM
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
 #pragma unroll
-        for (int k = 0; k < HS / 16; ++k)
-          ptx::mma_f16_ss(tS, ptx::make_smem_desc(q_s + k * 32, 16, 1024), ptx::make_smem_desc(sK + k * 32, 16, 1024),
-                          g.idesc_s, k > 0 ? 1u : 0u);
+        for (int kk = 0; kk < HS / 16; ++kk)
+          ptx::mma_f16_ss(tS, ptx::make_smem_desc(q_s + kk * 32, 16, 1024), ptx::make_smem_desc(sK + kk * 32, 16, 1024),
+                          g.idesc_s, kk > 0 ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < HS / 16; ++k)
-          ptx::mma_f16_ss(tDP, ptx::make_smem_desc(do_s + k * 32, 16, 1024), ptx::make_smem_desc(sV + k * 32, 16, 1024),
-                          g.idesc_s, k > 0 ? 1u : 0u);
+        for (int kk = 0; kk < HS / 16; ++kk)
+          ptx::mma_f16_ss(tDP, ptx::make_smem_desc(do_s + kk * 32, 16, 1024), ptx::make_smem_desc(sV + kk * 32, 16, 1024),
+                          g.idesc_s, kk > 0 ? 1u : 0u);
         ptx::mma_commit(bar(SDP_FULL));
       }
       __syncwarp();
+    };
+    issue_sdp(0);
+    for (int it = 0; it < n_it; ++it) {
+      const int st = it & 1; const uint32_t ph = it & 1;
       ptx::mbar_wait_conv(bar(PDS_FULL), ph);
-      ptx::mbar_wait_conv(bar(DQ_FREE), ph ^ 1u);
+      if (it + 1 < n_it) issue_sdp(it + 1);
+      ptx::mbar_wait_conv(bar(DQ_FREE), ph ^ 1u);       // dQ of step it-1 has been read out of TMEM
       ptx::tc_fence_after();
       if (ptx::elect_one()) {
 #pragma unroll
@@ -355,7 +383,7 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       }
       __syncwarp();
     }
-  } else if (warp == 6) {
+  } else if (warp == 10) {
     // ===== issuer B: dV += P^T dO, dK += dS^T Q (16 MMAs, both operands MN-major) =====
     ptx::mbar_wait_conv(bar(KV_FULL), 0);
     for (int it = 0; it < n_it; ++it) {
@@ -380,91 +408,108 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       __syncwarp();
     }
   } else {
+    // ===== warps 2-9: two threads per query row (warps w, w + 4 share a TMEM lane quadrant); each owns 64 of the 128 key
+    // columns of S / dP / P / dS, 32 of the 64 dQ columns, and one of dV / dK in the epilogue.  lse and D are per-row inputs,
+    // so the two threads never have to talk to each other. =====
     const int q = warp & 3;
+    const int hf = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    const uint32_t stg = sStg + (uint32_t)q * 8192u;
-    for (int it = 0; it < n_it; ++it) {
-      const uint32_t ph = it & 1;
-      const int i = jb + it;
-      const bool diag = (it == 0);
-      const size_t ridx = ((size_t)b * g.nh + h) * g.T + (size_t)i * FB + row;
-      const float lse_r = g.lse[ridx], d_r = g.dsum[ridx];
-      ptx::mbar_wait(bar(SDP_FULL), ph);
-      ptx::tc_fence_after();
-      ptx::mbar_wait(bar(PDS_FREE), ph ^ 1u);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t rs[32], rp[32];
-        ptx::tmem_ld_32x32(tS + lane_sel + c * 32, rs);
-        ptx::tmem_ld_32x32(tDP + lane_sel + c * 32, rp);
-        ptx::tmem_ld_wait();
-        float p[32], ds[32];
-#pragma unroll
-        for (int k = 0; k < 32; ++k) {
-          const float e = exp2f(__uint_as_float(rs[k]) * g.cs - lse_r);
-          p[k] = (!diag || c * 32 + k <= row) ? e : 0.f;
-          ds[k] = p[k] * (__uint_as_float(rp[k]) - d_r) * g.scale;
-        }
-        const uint32_t off = (uint32_t)(c >> 1) * (FB * 128) + (uint32_t)row * 128u;
-#pragma unroll
-        for (int j8 = 0; j8 < 4; ++j8) {
-          const uint32_t sw = (((uint32_t)((c & 1) * 4 + j8)) ^ (uint32_t)(row & 7)) << 4;
-          ptx::st_shared_16(sP + off + sw, pack8(&p[j8 * 8]));
-          ptx::st_shared_16(sDS + off + sw, pack8(&ds[j8 * 8]));
-        }
-      }
-      ptx::tc_fence_before();
-      ptx::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) { ptx::mbar_arrive(bar(SDP_FREE)); ptx::mbar_arrive(bar(PDS_FULL)); }
-      // dQ_i contribution of this key block: TMEM -> fp32 staging -> TMA reduce-add
-      ptx::mbar_wait(bar(DQ_FULL), ph);
+    const uint32_t stg = sStg + (uint32_t)(hf * 4 + q) * 4096u;       // 4 KB per warp: 32 x 32 fp32 (dQ) or 32 x 64 bf16 (dV / dK)
+    // dQ_i contribution of this key block: TMEM -> fp32 staging -> TMA reduce-add (this warp: rows q*32.., columns hf*32..)
+    auto dq_readout = [&](int k) {
+      ptx::mbar_wait(bar(DQ_FULL), (uint32_t)(k & 1));
       ptx::tc_fence_after();
       if (lane == 0) ptx::bulk_wait_read<0>();
       __syncwarp();
+      uint32_t raw[32];
+      ptx::tmem_ld_32x32(tDQ + lane_sel + hf * 32, raw);
+      ptx::tmem_ld_wait();
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(tDQ + lane_sel + hf * 32, raw);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int c16 = 0; c16 < 8; ++c16) {
-          const uint4 v = make_uint4(raw[c16 * 4], raw[c16 * 4 + 1], raw[c16 * 4 + 2], raw[c16 * 4 + 3]);
-          ptx::st_shared_16(stg + hf * 4096u + (uint32_t)lane * 128u + ((((uint32_t)c16) ^ (uint32_t)(lane & 7)) << 4), v);
-        }
+      for (int c16 = 0; c16 < 8; ++c16) {
+        const uint4 v = make_uint4(raw[c16 * 4], raw[c16 * 4 + 1], raw[c16 * 4 + 2], raw[c16 * 4 + 3]);
+        ptx::st_shared_16(stg + (uint32_t)lane * 128u + ((((uint32_t)c16) ^ (uint32_t)(lane & 7)) << 4), v);
       }
       ptx::tc_fence_before();
       ptx::fence_proxy_async();
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_arrive(bar(DQ_FREE));
-        const int grow = (int)(((size_t)b * g.nh + h) * g.T) + i * FB + q * 32;
-        ptx::tma_reduce_add_2d(&tma_dq, stg, 0, grow);
-        ptx::tma_reduce_add_2d(&tma_dq, stg + 4096u, 32, grow);
+        const int grow = (int)(((size_t)b * g.nh + h) * g.T) + (jb + k) * FB + q * 32;
+        ptx::tma_reduce_add_2d(&tma_dq, stg, hf * 32, grow);
         ptx::bulk_commit();
       }
+    };
+    for (int it = 0; it < n_it; ++it) {
+      const uint32_t ph = it & 1;
+      const int i = jb + it;
+      const bool diag = (it == 0);
+      const size_t ridx = ((size_t)b * g.nh + h) * g.T + (size_t)i * FB + row;
+      const float lse_r = g.lse[ridx], d_r = g.dsum[ridx];
+      const int lim = row - hf * 64;               // diagonal block: column k of this half is visible iff k <= lim
+      ptx::mbar_wait(bar(SDP_FULL), ph);
+      ptx::tc_fence_after();
+      bf16x8 pp[8], dd[8];                         // this thread's 64 P and 64 dS values, packed: computed before P / dS are free
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        uint32_t rs[32], rp[32];
+        ptx::tmem_ld_32x32(tS + lane_sel + hf * 64 + c * 32, rs);
+        ptx::tmem_ld_32x32(tDP + lane_sel + hf * 64 + c * 32, rp);
+        ptx::tmem_ld_wait();
+        float p[32], ds[32];
+        if (diag) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const float e = exp2f(__uint_as_float(rs[k]) * g.cs - lse_r);
+            p[k] = (c * 32 + k <= lim) ? e : 0.f;
+            ds[k] = p[k] * (__uint_as_float(rp[k]) - d_r) * g.scale;
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            p[k] = exp2f(__uint_as_float(rs[k]) * g.cs - lse_r);
+            ds[k] = p[k] * (__uint_as_float(rp[k]) - d_r) * g.scale;
+          }
+        }
+#pragma unroll
+        for (int j8 = 0; j8 < 4; ++j8) { pp[c * 4 + j8] = pack8(&p[j8 * 8]); dd[c * 4 + j8] = pack8(&ds[j8 * 8]); }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(SDP_FREE));        // S / dP may be overwritten by step it+1
+      ptx::mbar_wait(bar(PDS_FREE), ph ^ 1u);                // the 24 MMAs that read P / dS of step it-1 have retired
+      const uint32_t off = (uint32_t)hf * (FB * 128) + (uint32_t)row * 128u;
+#pragma unroll
+      for (int j8 = 0; j8 < 8; ++j8) {
+        const uint32_t sw = (((uint32_t)j8) ^ (uint32_t)(row & 7)) << 4;
+        ptx::st_shared_16(sP + off + sw, pp[j8]);
+        ptx::st_shared_16(sDS + off + sw, dd[j8]);
+      }
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(bar(PDS_FULL));
+      if (it > 0) dq_readout(it - 1);              // deferred by one step: dQ_{it-1} was issued after S / dP of this step
     }
-    // epilogue: dV_j, dK_j (rows = keys) -> bf16 -> staging -> TMA store into the K / V slices of dqkv
+    dq_readout(n_it - 1);
+    // epilogue: dV_j (hf = 0) or dK_j (hf = 1), rows = keys -> bf16 -> staging -> TMA store into the V / K slice of dqkv
     ptx::mbar_wait(bar(DKV_DONE), 0);
     ptx::tc_fence_after();
     if (lane == 0) ptx::bulk_wait_read<0>();
     __syncwarp();
+    {
+      const uint32_t src = hf == 0 ? tDV : tDK;
+      const uint32_t dst = stg + (uint32_t)lane * 128u;
 #pragma unroll
-    for (int which = 0; which < 2; ++which) {
-      const uint32_t src = which == 0 ? tDV : tDK;
-      const uint32_t dst = stg + (uint32_t)which * 4096u + (uint32_t)lane * 128u;
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
+      for (int c = 0; c < 2; ++c) {
         uint32_t raw[32];
-        ptx::tmem_ld_32x32(src + lane_sel + hf * 32, raw);
+        ptx::tmem_ld_32x32(src + lane_sel + c * 32, raw);
         ptx::tmem_ld_wait();
 #pragma unroll
         for (int j8 = 0; j8 < 4; ++j8) {
           float t[8];
 #pragma unroll
           for (int k = 0; k < 8; ++k) t[k] = __uint_as_float(raw[j8 * 8 + k]);
-          ptx::st_shared_16(dst + ((((uint32_t)(hf * 4 + j8)) ^ (uint32_t)(lane & 7)) << 4), pack8(t));
+          ptx::st_shared_16(dst + ((((uint32_t)(c * 4 + j8)) ^ (uint32_t)(lane & 7)) << 4), pack8(t));
         }
       }
     }
@@ -472,8 +517,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
     ptx::fence_proxy_async();
     __syncwarp();
     if (lane == 0) {
-      ptx::tma_store_4d(&tma_dv, stg, 0, jb * FB + q * 32, h, b);
-      ptx::tma_store_4d(&tma_dk, stg + 4096u, 0, jb * FB + q * 32, h, b);
+      if (hf == 0) ptx::tma_store_4d(&tma_dv, stg, 0, jb * FB + q * 32, h, b);
+      else ptx::tma_store_4d(&tma_dk, stg, 0, jb * FB + q * 32, h, b);
       ptx::bulk_commit();
       ptx::bulk_wait_read<0>();
     }
