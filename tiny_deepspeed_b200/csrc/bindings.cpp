@@ -303,7 +303,7 @@ Tensor flash_bwd_(const Tensor& dy, const Tensor& qkv, const Tensor& y, const Te
   Tensor dqkv = torch::empty_like(qkv);
   auto fopt = qkv.options().dtype(at::kFloat);
   Tensor dsum = torch::empty({B, n_head, T}, fopt);
-  Tensor dq_ws = torch::empty({B, n_head, T, hs}, fopt);
+  Tensor dq_ws = torch::empty({3, B, n_head, T, hs}, fopt);      // dQ, dK, dV fp32 workspaces (flash_sm100.cu)
   flash_bwd(qkv.data_ptr(), y.data_ptr(), dy.data_ptr(), lse.data_ptr<float>(), dsum.data_ptr<float>(),
             dq_ws.data_ptr<float>(), dqkv.data_ptr(), B, T, (int)n_head, 1.0f / sqrtf((float)hs), cur_stream());
   check_launch("flash_bwd");

@@ -279,6 +279,7 @@ struct FlashBwdDev {
   float cs, scale;
   const float* lse;    // [B, nh, T] log2 domain
   const float* dsum;   // [B, nh, T]  D = rowsum(dO o O)
+  int n_split;         // key blocks jb < n_split are processed by two CTAs (half of the query range each)
   uint32_t idesc_s, idesc_dkv, idesc_dq;
 };
 
@@ -286,7 +287,8 @@ __global__ void __launch_bounds__(kFBThreads, 1)
 flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_k,
                  const __grid_constant__ CUtensorMap tma_v, const __grid_constant__ CUtensorMap tma_do,
                  const __grid_constant__ CUtensorMap tma_dk, const __grid_constant__ CUtensorMap tma_dv,
-                 const __grid_constant__ CUtensorMap tma_dq, const __grid_constant__ FlashBwdDev g) {
+                 const __grid_constant__ CUtensorMap tma_dq, const __grid_constant__ CUtensorMap tma_dkw,
+                 const __grid_constant__ CUtensorMap tma_dvw, const __grid_constant__ FlashBwdDev g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t sK = base, sV = sK + kTileQK;
@@ -302,9 +304,24 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - ptx::smem_u32(smem_raw)));
 
   const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
-  const int jb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;     // jb = 0 has the most query blocks: scheduled first
+  // Work items.  Key block jb meets the query blocks i >= jb: nq - jb steps, 8 for jb = 0 but 1 for the last one, and the launch
+  // is as long as its longest CTA.  The key blocks with more than ceil(nq / 2) steps are therefore split into two CTAs that take
+  // half of the query range each and add their fp32 dK / dV partials into a workspace (TMA reduce-add, converted together with
+  // dQ); the rest store bf16 dK / dV directly.  T = 1024: 12 CTAs per head with at most 4 steps instead of 8 with up to 8.
+  const int h = blockIdx.y, b = blockIdx.z;
   const int nq = g.T / FB;
-  const int n_it = nq - jb;
+  const int n_split = g.n_split;                  // key blocks jb < n_split are split (host: nq - ceil(nq / 2))
+  int jb, it0, n_it;
+  bool split;
+  if ((int)blockIdx.x < 2 * n_split) {
+    jb = (int)blockIdx.x >> 1;
+    const int n_all = nq - jb, h0 = (n_all + 1) / 2;
+    split = true;
+    if (blockIdx.x & 1) { it0 = h0; n_it = n_all - h0; } else { it0 = 0; n_it = h0; }
+  } else {
+    jb = (int)blockIdx.x - n_split; it0 = 0; n_it = nq - jb; split = false;
+  }
+  const int i_base = jb + it0;                    // first query block of this CTA
   pdl_launch();
 
   if (warp == 0 && ptx::elect_one()) {
@@ -335,8 +352,8 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
         const int st = it & 1; const uint32_t ph2 = (it >> 1) & 1;
         ptx::mbar_wait_conv(bar(QDO_EMPTY + st), ph2 ^ 1u);
         ptx::mbar_expect_tx(bar(QDO_FULL + st), 2 * kTileQK);
-        ptx::tma_load_4d(sQ + st * kTileQK, &tma_q, bar(QDO_FULL + st), 0, (jb + it) * FB, h, b);
-        ptx::tma_load_4d(sDO + st * kTileQK, &tma_do, bar(QDO_FULL + st), 0, (jb + it) * FB, h, b);
+        ptx::tma_load_4d(sQ + st * kTileQK, &tma_q, bar(QDO_FULL + st), 0, (i_base + it) * FB, h, b);
+        ptx::tma_load_4d(sDO + st * kTileQK, &tma_do, bar(QDO_FULL + st), 0, (i_base + it) * FB, h, b);
       }
     }
   } else if (warp == 1) {
@@ -435,15 +452,15 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       __syncwarp();
       if (lane == 0) {
         ptx::mbar_arrive(bar(DQ_FREE));
-        const int grow = (int)(((size_t)b * g.nh + h) * g.T) + (jb + k) * FB + q * 32;
+        const int grow = (int)(((size_t)b * g.nh + h) * g.T) + (i_base + k) * FB + q * 32;
         ptx::tma_reduce_add_2d(&tma_dq, stg, hf * 32, grow);
         ptx::bulk_commit();
       }
     };
     for (int it = 0; it < n_it; ++it) {
       const uint32_t ph = it & 1;
-      const int i = jb + it;
-      const bool diag = (it == 0);
+      const int i = i_base + it;
+      const bool diag = (i == jb);
       const size_t ridx = ((size_t)b * g.nh + h) * g.T + (size_t)i * FB + row;
       const float lse_r = g.lse[ridx], d_r = g.dsum[ridx];
       const int lim = row - hf * 64;               // diagonal block: column k of this half is visible iff k <= lim
@@ -491,13 +508,14 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
       if (it > 0) dq_readout(it - 1);              // deferred by one step: dQ_{it-1} was issued after S / dP of this step
     }
     dq_readout(n_it - 1);
-    // epilogue: dV_j (hf = 0) or dK_j (hf = 1), rows = keys -> bf16 -> staging -> TMA store into the V / K slice of dqkv
+    // epilogue: dV_j (hf = 0) or dK_j (hf = 1), rows = keys
     ptx::mbar_wait(bar(DKV_DONE), 0);
     ptx::tc_fence_after();
-    if (lane == 0) ptx::bulk_wait_read<0>();
-    __syncwarp();
-    {
-      const uint32_t src = hf == 0 ? tDV : tDK;
+    const uint32_t src = hf == 0 ? tDV : tDK;
+    if (!split) {
+      // whole key block in this CTA: -> bf16 -> staging -> TMA store into the V / K slice of dqkv
+      if (lane == 0) ptx::bulk_wait_read<0>();
+      __syncwarp();
       const uint32_t dst = stg + (uint32_t)lane * 128u;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
@@ -512,15 +530,39 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
           ptx::st_shared_16(dst + ((((uint32_t)(c * 4 + j8)) ^ (uint32_t)(lane & 7)) << 4), pack8(t));
         }
       }
-    }
-    ptx::tc_fence_before();
-    ptx::fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) {
-      if (hf == 0) ptx::tma_store_4d(&tma_dv, stg, 0, jb * FB + q * 32, h, b);
-      else ptx::tma_store_4d(&tma_dk, stg, 0, jb * FB + q * 32, h, b);
-      ptx::bulk_commit();
-      ptx::bulk_wait_read<0>();
+      ptx::tc_fence_before();
+      ptx::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) {
+        if (hf == 0) ptx::tma_store_4d(&tma_dv, stg, 0, jb * FB + q * 32, h, b);
+        else ptx::tma_store_4d(&tma_dk, stg, 0, jb * FB + q * 32, h, b);
+        ptx::bulk_commit();
+        ptx::bulk_wait_read<0>();
+      }
+    } else {
+      // half of the query range: fp32 partial -> staging (32 x 32 slabs) -> TMA reduce-add into the dK / dV workspace
+      const int grow = (int)(((size_t)b * g.nh + h) * g.T) + jb * FB + q * 32;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        if (lane == 0) ptx::bulk_wait_read<0>();
+        __syncwarp();
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(src + lane_sel + c * 32, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c16 = 0; c16 < 8; ++c16) {
+          const uint4 v = make_uint4(raw[c16 * 4], raw[c16 * 4 + 1], raw[c16 * 4 + 2], raw[c16 * 4 + 3]);
+          ptx::st_shared_16(stg + (uint32_t)lane * 128u + ((((uint32_t)c16) ^ (uint32_t)(lane & 7)) << 4), v);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+          ptx::tma_reduce_add_2d(hf == 0 ? &tma_dvw : &tma_dkw, stg, c * 32, grow);
+          ptx::bulk_commit();
+        }
+      }
+      ptx::tc_fence_before();
+      if (lane == 0) ptx::bulk_wait_read<0>();
     }
     __syncwarp();
   }
@@ -531,16 +573,22 @@ flash_bwd_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constan
 }
 
 // D[b,h,t] = sum_d dO[b,t,h,d] * O[b,t,h,d]   (one thread per (b,t,h): 8 x 16-byte loads from each tensor)
-// Also clears the fp32 dQ workspace (8 floats per thread: the grids coincide) — one graph node less per layer than a memset.
+// Also clears the fp32 dQ / dK / dV workspaces (3 x 8 floats per thread: the grids coincide) — one graph node less per layer
+// than a memset.
 __global__ void flash_dsum_kernel(const __nv_bfloat16* __restrict__ dout, const __nv_bfloat16* __restrict__ out,
-                                  float* __restrict__ dsum, float* __restrict__ dq_ws, int B, int T, int nh) {
+                                  float* __restrict__ dsum, float* __restrict__ dq_ws, int B, int T, int nh, int t_split) {
   pdl_launch(); pdl_wait();
   {
     const size_t gid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (gid0 < (size_t)B * T * nh * 8) {
-      float4* z = reinterpret_cast<float4*>(dq_ws) + gid0 * 2;
-      z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-      z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const size_t n8 = (size_t)B * T * nh * 8;
+    if (gid0 < n8) {
+      // workspace rows are (b, h, t): dK / dV partial sums exist only for the split key blocks, t < t_split
+      const int nw = (int)((gid0 >> 3) % (size_t)T) < t_split ? 3 : 1;
+      for (int w = 0; w < nw; ++w) {
+        float4* z = reinterpret_cast<float4*>(dq_ws) + ((size_t)w * n8 + gid0) * 2;
+        z[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+        z[1] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   // 8 lanes per (b,t,h) row: one 16-byte load from each tensor per lane (fully coalesced), 3-step shuffle reduce
@@ -564,31 +612,39 @@ __global__ void flash_dsum_kernel(const __nv_bfloat16* __restrict__ dout, const 
   if (ok && v8 == 0) dsum[((size_t)bb * nh + hh) * T + t] = acc;
 }
 
-// dq workspace fp32 [B, nh, T, 64] -> bf16 into dqkv[:, :, h*64 : h*64+64]
-__global__ void flash_dq_convert_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ dqkv, int B, int T, int nh) {
+// workspaces fp32 [3][B, nh, T, 64] (dQ, dK, dV) -> bf16 into the Q / K / V slices of dqkv: dQ for every row, dK / dV for the
+// key rows t < t_split whose key blocks were split over two CTAs (the others were stored by the backward kernel itself)
+__global__ void flash_dq_convert_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ dqkv, int B, int T, int nh, int t_split) {
   pdl_launch(); pdl_wait();
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;       // one thread per 8 output elements
   const int per_row = HS / 8;
   if (idx >= B * nh * T * per_row) return;
   const int v8 = idx % per_row;
   const int t = (idx / per_row) % T, hh = (idx / (per_row * T)) % nh, bb = idx / (per_row * T * nh);
-  const float* src = ws + (((size_t)bb * nh + hh) * T + t) * HS + v8 * 8;
-  const float4 a = reinterpret_cast<const float4*>(src)[0], c = reinterpret_cast<const float4*>(src)[1];
-  float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
-  st8(dqkv + ((size_t)bb * T + t) * (size_t)(3 * nh * HS) + (size_t)hh * HS + v8 * 8, pack8(f));
+  const size_t n_ws = (size_t)B * nh * T * HS;
+  const int C = nh * HS;
+  const int nw = t < t_split ? 3 : 1;
+  for (int w = 0; w < nw; ++w) {
+    const float* src = ws + (size_t)w * n_ws + (((size_t)bb * nh + hh) * T + t) * HS + v8 * 8;
+    const float4 a = reinterpret_cast<const float4*>(src)[0], c = reinterpret_cast<const float4*>(src)[1];
+    float f[8] = {a.x, a.y, a.z, a.w, c.x, c.y, c.z, c.w};
+    st8(dqkv + ((size_t)bb * T + t) * (size_t)(3 * C) + (size_t)w * C + (size_t)hh * HS + v8 * 8, pack8(f));
+  }
 }
 
 }  // namespace
 
 bool flash_supported(int T, int hs) { return hs == HS && T % FB == 0 && T >= FB; }
 
-// dqkv receives dK, dV (TMA stores) and dQ (converted from the fp32 workspace `dq_ws`, which this call zeroes)
+// dqkv receives dK, dV (TMA stores, or converted fp32 partial sums for the split key blocks) and dQ (converted from the fp32
+// workspace).  `dq_ws`: 3 x [B, nh, T, 64] floats (dQ, dK, dV), zeroed by this call.
 void flash_bwd(const void* qkv, const void* y, const void* dy, const float* lse, float* dsum, float* dq_ws, void* dqkv,
                int B, int T, int nh, float scale, cudaStream_t stream) {
   const int C = nh * HS;
   const __nv_bfloat16* base = reinterpret_cast<const __nv_bfloat16*>(qkv);
   __nv_bfloat16* dbase = reinterpret_cast<__nv_bfloat16*>(dqkv);
-  CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq;
+  CUtensorMap tq, tk, tv, tdo, tdk, tdv, tdq, tdkw, tdvw;
+  const size_t n_ws = (size_t)B * nh * T * HS;
   auto view = [&](const void* p, int64_t ld, int64_t bs) { return GemmOperand{p, ld, bs, (int64_t)HS, false}; };
   bool ok = make_map(&tq, view(base, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, FB) &&
             make_map(&tk, view(base + C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, FB) &&
@@ -596,22 +652,28 @@ void flash_bwd(const void* qkv, const void* y, const void* dy, const float* lse,
             make_map(&tdo, view(dy, C, (int64_t)T * C), T, HS, B, nh, FB) &&
             make_map(&tdk, view(dbase + C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, 32) &&
             make_map(&tdv, view(dbase + 2 * C, 3 * C, (int64_t)T * 3 * C), T, HS, B, nh, 32) &&
-            make_map_f32_2d(&tdq, dq_ws, (int64_t)B * nh * T, HS, HS, 32, 32);
+            make_map_f32_2d(&tdq, dq_ws, (int64_t)B * nh * T, HS, HS, 32, 32) &&
+            make_map_f32_2d(&tdkw, dq_ws + n_ws, (int64_t)B * nh * T, HS, HS, 32, 32) &&
+            make_map_f32_2d(&tdvw, dq_ws + 2 * n_ws, (int64_t)B * nh * T, HS, HS, 32, 32);
   if (!ok) { fprintf(stderr, "[tds] flash_bwd: tensor map creation failed\n"); abort(); }
   static_assert(HS == 64, "flash_dsum_kernel clears 8 floats of the dQ workspace per thread (8 threads per row of 64)");
+  // TDS_FLASH_SPLIT=0: one CTA per key block (no dK / dV workspace traffic); default: split the long key blocks in two
+  static const bool want_split = !(getenv("TDS_FLASH_SPLIT") && atoi(getenv("TDS_FLASH_SPLIT")) == 0);
+  const int nq = T / FB, n_split = want_split ? nq - (nq + 1) / 2 : 0;
   const int nthreads = B * T * nh * 8;
   launch_k(flash_dsum_kernel, dim3((nthreads + 255) / 256), dim3(256), 0, stream, (const __nv_bfloat16*)dy,
-           (const __nv_bfloat16*)y, dsum, dq_ws, B, T, nh);
+           (const __nv_bfloat16*)y, dsum, dq_ws, B, T, nh, n_split * FB);
   FlashBwdDev g;
+  g.n_split = n_split;
   g.T = T; g.nh = nh; g.cs = scale * 1.4426950408889634f; g.scale = scale; g.lse = lse; g.dsum = dsum;
   g.idesc_s = make_idesc_bf16(FB, FB, false, false);
   g.idesc_dkv = make_idesc_bf16(FB, HS, true, true);
   g.idesc_dq = make_idesc_bf16(FB, HS, false, true);
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(flash_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBwdSmem); attr = true; }
-  launch_k(flash_bwd_kernel, dim3(T / FB, nh, B), dim3(kFBThreads), kBwdSmem, stream, tq, tk, tv, tdo, tdk, tdv, tdq, g);
+  launch_k(flash_bwd_kernel, dim3(nq + n_split, nh, B), dim3(kFBThreads), kBwdSmem, stream, tq, tk, tv, tdo, tdk, tdv, tdq, tdkw, tdvw, g);
   const int nconv = B * nh * T * (HS / 8);
-  launch_k(flash_dq_convert_kernel, dim3((nconv + 255) / 256), dim3(256), 0, stream, (const float*)dq_ws, dbase, B, T, nh);
+  launch_k(flash_dq_convert_kernel, dim3((nconv + 255) / 256), dim3(256), 0, stream, (const float*)dq_ws, dbase, B, T, nh, n_split * FB);
 }
 
 void flash_fwd(const void* qkv, void* y, float* lse, int B, int T, int nh, float scale, cudaStream_t stream) {
