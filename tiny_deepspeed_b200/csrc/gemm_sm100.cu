@@ -37,7 +37,11 @@ constexpr int BM = 128;       // UMMA M (cta_group::1)
 constexpr int BK = 64;        // one 128-byte swizzle row of bf16
 constexpr int UK = 16;        // UMMA K for 16-bit inputs
 constexpr int kThreads = 192;        // single pipeline: producer, issuer, 4 epilogue warps
-constexpr int kThreadsDual = 256;    // dual pipeline: 2 x (producer, issuer), 4 epilogue warps
+// Epilogue warps: 4 (one per TMEM lane quadrant), or 8 on the FAST (bf16 TMA-store) kernels — two warps per quadrant, each
+// taking 32 of a slab's 64 columns.  At one tile per CTA the epilogue is pure critical path, and with one warp per scheduler
+// it ran at ~1/3 instruction per cycle (profiles/r2_gemm_epitrace_before.log: 1900 cycles for a 128 x 64 tile).
+constexpr int epi_warps(bool fast) { return fast ? 8 : 4; }
+constexpr int gemm_threads(int np, bool fast) { return 32 * (2 * np + epi_warps(fast)); }
 constexpr uint32_t kStageBufBytes = 4096;   // one 32-row x 64-col bf16 slab, SWIZZLE_128B
 
 enum { EPI_NONE = 0, EPI_GELU_SAVE = 1, EPI_GELU_BWD = 2, EPI_RESIDUAL = 3 };
@@ -123,7 +127,7 @@ __device__ __forceinline__ float ld1_any(const void* base, long long idx, int f3
 // FAST = the output goes registers -> swizzled smem -> TMA store and nothing else is compiled in (bf16 out, aligned, no
 //        accumulate: every GEMM of the bf16 training step); the generic instantiations keep the direct-store paths
 template <int BN, bool F32, bool RED, int NP, int EPI, bool FAST>
-__global__ void __launch_bounds__(32 * (2 * NP + 4), 1)
+__global__ void __launch_bounds__(gemm_threads(NP, FAST), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
             const __grid_constant__ GemmDev g) {
@@ -175,7 +179,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
     // a smem stage is refilled by EVERY CTA of the cluster (B slices are multicast), so it is free only when all
     // cm MMA issuers have released it
     for (int s = 0; s < C::kStages; ++s) { ptx::mbar_init(full_bar(s), 1); ptx::mbar_init(empty_bar(s), (uint32_t)g.cm); }
-    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), kHalves); ptx::mbar_init(tempty_bar(s), 4); }
+    for (int s = 0; s < 2; ++s) { ptx::mbar_init(tfull_bar(s), kHalves); ptx::mbar_init(tempty_bar(s), (uint32_t)epi_warps(FAST)); }
     for (int w = 0; w < 4; ++w)
       for (int i = 0; i < NB; ++i) ptx::mbar_init(aux_bar(w, i), 1);
     ptx::fence_mbar_init();
@@ -329,6 +333,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
   } else {
     // ===================== epilogue warps =====================
     const int q = warp & 3;                      // TMEM lane quadrant this warp may access
+    constexpr int EW = epi_warps(FAST);
+    constexpr bool kSplit = EW == 8;              // two warps per quadrant: this one takes column half `hf` of every 64-column slab
+    const int hf = kSplit ? ((warp - kEpiWarp0) >> 2) : 0;
+    auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
     int local = 0;
     uint32_t sbuf_toggle = 0;
     const uint32_t my_stage0 = sStage + (uint32_t)q * (uint32_t)NB * kStageBufBytes;   // NB 4 KB staging buffers per warp
@@ -343,7 +351,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
       constexpr long long kChunk = 4096;
       const long long nchunk = (g.pf_bytes + kChunk - 1) / kChunk;
       const int e = (warp - kEpiWarp0) * 32 + lane;
-      for (long long c = (long long)blockIdx.x + (long long)gridDim.x * e; c < nchunk; c += (long long)gridDim.x * 128) {
+      for (long long c = (long long)blockIdx.x + (long long)gridDim.x * e; c < nchunk; c += (long long)gridDim.x * (EW * 32)) {
         const long long left = g.pf_bytes - c * kChunk;
         ptx::prefetch_l2_bulk(g.pf + c * kChunk, (uint32_t)(left < kChunk ? left : kChunk));
       }
@@ -367,7 +375,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
         if (n_slabs > BN / 64) n_slabs = BN / 64;
         if (dbg & 4) n_slabs = 0;
       }
-      if (aux_in && lane == 0) {
+      if (aux_in && lane == 0 && hf == 0) {
         ptx::bulk_wait_read<0>();                 // the previous tile's stores have left the buffers
         for (int sl = 0; sl < n_slabs && sl < NB; ++sl) {
           ptx::mbar_expect_tx(aux_bar(q, sl), kStageBufBytes);
@@ -448,33 +456,32 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             dbuf = my_stage0 + sbuf_toggle * 2u * kStageBufBytes;
             abuf = dbuf + kStageBufBytes;
             if (++sbuf_toggle == (uint32_t)kPairs) sbuf_toggle = 0;
-            if (lane == 0) ptx::bulk_wait_read<kPairs - 1>();
-            __syncwarp();
+            if (lane == 0) ptx::bulk_wait_read<kPairs - 1>();      // only the storing warp (hf = 0) has groups in flight
+            if (kSplit) pair_sync(); else __syncwarp();
             if (etr) et[1] = clock64();
           } else {
             dbuf = my_stage0 + sbuf_toggle * kStageBufBytes;
             if (++sbuf_toggle == (uint32_t)NB) sbuf_toggle = 0;
             if (lane == 0) ptx::bulk_wait_read<NB - 1>();
-            __syncwarp();
+            if (kSplit) pair_sync(); else __syncwarp();
             if (etr) et[1] = clock64();
           }
           // bias of the slab's 64 columns: 8 x 16 B at the same address in every lane (one broadcast transaction each), issued
           // BEFORE the accumulator loads so their latency hides under them.  Columns past N are clipped by the TMA store,
           // so the address is only clamped; no bias = add zeros.  (The previous form — a guarded 4 x 32-bit load per 8
           // columns, then a branch per operand source — serialised eight load latencies per slab: profiles/r2_gemm_epilogue.md)
-          uint4 braw[8];
+          auto do_half = [&](const int half) {     // 32 of the slab's 64 columns (`half` is a compile-time constant at each call)
+            uint4 braw[4];
 #pragma unroll
-          for (int j8 = 0; j8 < 8; ++j8) braw[j8] = make_uint4(0u, 0u, 0u, 0u);
-          if (g.bias) {
+            for (int j8 = 0; j8 < 4; ++j8) braw[j8] = make_uint4(0u, 0u, 0u, 0u);
+            if (g.bias) {
 #pragma unroll
-            for (int j8 = 0; j8 < 8; ++j8) {
-              int nc = ns + j8 * 8;
-              nc = nc > g.N - 8 ? g.N - 8 : nc;
-              braw[j8] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.bias) + nc));
+              for (int j8 = 0; j8 < 4; ++j8) {
+                int nc = ns + half * 32 + j8 * 8;
+                nc = nc > g.N - 8 ? g.N - 8 : nc;
+                braw[j8] = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(g.bias) + nc));
+              }
             }
-          }
-#pragma unroll
-          for (int half = 0; half < 2; ++half) {
             // this thread's 4 x 16 B of the residual / pre-activation slab (same swizzled chunks the result goes back to)
             uint4 ax[4];
             if (aux_in) {
@@ -493,7 +500,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
             for (int j8 = 0; j8 < 4; ++j8) {
               const int nc = nb + j8 * 8;
               {
-                float bf[8]; unpack8(*reinterpret_cast<const bf16x8*>(&braw[half * 4 + j8]), bf);
+                float bf[8]; unpack8(*reinterpret_cast<const bf16x8*>(&braw[j8]), bf);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j8 * 8 + j] += bf[j];
               }
@@ -520,16 +527,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ C
               ptx::st_shared_16(dbuf + chunk, pack8(&v[j8 * 8]));
             }
             if (etr) et[3 + half * 2] = clock64();
+          };
+          if (kSplit) {
+            if (hf == 0) do_half(0); else do_half(1);
+          } else {
+            do_half(0);
+            do_half(1);
           }
           ptx::fence_proxy_async();     // generic-proxy smem writes -> visible to the TMA (async proxy)
-          __syncwarp();
+          if (kSplit) pair_sync(); else __syncwarp();     // both column halves of the slab are in the staging buffer
           if (etr) et[6] = clock64();
-          if (lane == 0 && m0 + q * 32 < g.M && !(dbg & 1)) {
+          if (lane == 0 && hf == 0 && m0 + q * 32 < g.M && !(dbg & 1)) {
             ptx::tma_store_4d(&tma_d, dbuf, ns, m0 + q * 32, b2, b1);
             if (gelu_save) ptx::tma_store_4d(&tma_aux, abuf, ns, m0 + q * 32, 0, 0);
             ptx::bulk_commit();
           }
-          if (aux_in && slab + NB < n_slabs && lane == 0) {
+          if (aux_in && slab + NB < n_slabs && lane == 0 && hf == 0) {
             // more slabs than buffers (BN = 256, or the runtime-epilogue kernels): recycle this buffer for slab + NB
             ptx::bulk_wait_read<0>();
             ptx::mbar_expect_tx(aux_bar(q, slab % NB), kStageBufBytes);
@@ -793,7 +806,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   }
   if (g.cm == 1) {
     const int grid = tiles < g_num_sms ? tiles : g_num_sms;
-    launch_k(gemm_kernel<BN, F32, RED, NP, EPI, FAST>, dim3(grid), dim3(32 * (2 * NP + 4)), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
+    launch_k(gemm_kernel<BN, F32, RED, NP, EPI, FAST>, dim3(grid), dim3(gemm_threads(NP, FAST)), Cfg<BN>::kSmem, s, ta, tb, td, tx, g);
     return;
   }
   // cluster launch: cm consecutive CTAs = cm consecutive M tiles of one N tile; grid is a whole number of clusters
@@ -802,7 +815,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
   if (clusters > cap) clusters = cap;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(clusters * g.cm);
-  cfg.blockDim = dim3(32 * (2 * NP + 4));
+  cfg.blockDim = dim3(gemm_threads(NP, FAST));
   cfg.dynamicSmemBytes = Cfg<BN>::kSmem;
   cfg.stream = s;
   cudaLaunchAttribute at[2];
