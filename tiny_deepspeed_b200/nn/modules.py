@@ -44,6 +44,11 @@ def _grad_of(policy, param, compute, rows=None):
 # wave of latency-bound CTAs — so dW is launched on a side stream while dX runs on the current one (fork/join inside
 # the captured graph).  TDS_DUAL_STREAM=0 restores the serial order.
 _DUAL = os.environ.get("TDS_DUAL_STREAM", "1") != "0"
+# TDS_SERIAL_BWD lists sites ("mlp_proj", "mlp_fc", "linear") that run dW then dX on one stream instead.  The kernel timeline
+# suggested it for the MLP down-projection (its dX next to its dW shows as 23-28 us against ~8 + ~11 us back to back: the two
+# single-wave kernels cannot share an SM), but the step says otherwise — none 3.115, mlp_proj 3.121, +mlp_fc 3.136,
+# all 3.174 ms (profiles/r2_step_sweeps.md) — so the default is empty.
+_SERIAL_SITES = set(filter(None, os.environ.get("TDS_SERIAL_BWD", "").split(",")))
 _side_streams = {}
 
 
@@ -56,9 +61,9 @@ def _side_stream(t: torch.Tensor):
     return _side_streams[key]
 
 
-def _linear_backward(pol, weight, shape, dy, x, tuner, dx_fn):
+def _linear_backward(pol, weight, shape, dy, x, tuner, dx_fn, site="linear"):
     """``dW`` (into the policy's gradient buffer) and ``dx_fn()`` (the dX GEMM); concurrent when possible."""
-    side = _side_stream(dy) if weight.requires_grad else None
+    side = _side_stream(dy) if weight.requires_grad and site not in _SERIAL_SITES else None
     if side is None:
         if weight.requires_grad:
             _grad_of(pol, weight, lambda out, acc: ops.linear_weight_grad(
@@ -187,7 +192,7 @@ class _MLPFn(torch.autograd.Function):
             pp.release(proj.weight, w)
             return d
 
-        dpre = _linear_backward(pp, proj.weight, (proj.out_features, proj.in_features), dy, act, None, dpre_fn)
+        dpre = _linear_backward(pp, proj.weight, (proj.out_features, proj.in_features), dy, act, None, dpre_fn, site="mlp_proj")
         if fc.bias is not None:
             _grad_of(pf, fc.bias, lambda out, acc: ops.linear_bias_grad(dpre, out=out, accumulate=acc))
 
@@ -200,7 +205,7 @@ class _MLPFn(torch.autograd.Function):
             pf.release(fc.weight, w)
             return d
 
-        dx = _linear_backward(pf, fc.weight, (fc.out_features, fc.in_features), dpre, x, None, dx_fn)
+        dx = _linear_backward(pf, fc.weight, (fc.out_features, fc.in_features), dpre, x, None, dx_fn, site="mlp_fc")
         return dx, None, None, (dy if ctx.has_res else None)
 
 
