@@ -397,6 +397,7 @@ PYBIND11_MODULE(TORCH_EXTENSION_NAME, m) {
   m.doc() = "tiny_deepspeed_b200 sm_100a kernels";
   m.def("gemm", &gemm, "persistent tcgen05 GEMM");
   m.def("gemm_set_prefetch", &gemm_set_prefetch, "one-shot L2 prefetch hint for the next gemm launch");
+  m.def("set_pdl", [](bool on) { set_pdl_enabled(on); }, "programmatic-dependent-launch edges between our kernels on / off");
   m.def("gemm_num_configs", &gemm_num_configs);
   m.def("set_gemm_pair", &set_gemm_pair, "route eligible GEMMs through the cta_group::2 kernel (0/1)");
   m.def("gemm_set_prof", &gemm_set_prof_t, "install / clear the per-CTA phase timestamp buffer (tools/gemm_timeline.py)");

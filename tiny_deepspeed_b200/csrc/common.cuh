@@ -20,13 +20,16 @@ namespace tds {
 TDS_DEVICE void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 TDS_DEVICE void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-inline bool pdl_enabled() {
-  // Round 1 (4.87 ms step, kernels 10-30 us): 4.98 ms with PDL edges, so it was opt-in.  Round 2 (3.3 ms step, GEMMs of
-  // 6-10 us whose barrier init / TMEM alloc / descriptor prefetch are ~1 us of prologue): 3.30 -> 3.24 ms with the edges
-  // (profiles/r2_step_sweeps.md), so it is ON unless TDS_PDL=0; the griddepcontrol instructions are no-ops without it
-  static const bool on = !(getenv("TDS_PDL") && atoi(getenv("TDS_PDL")) == 0);
+// Round 1 (4.87 ms step, kernels of 10-30 us): 4.98 ms with PDL edges.  Round 2, one GPU (3.2 ms step, GEMMs of 6-10 us whose
+// barrier init / TMEM alloc / descriptor prefetch are ~1 us of prologue): 3.214 -> 3.190 ms, so the edges are ON by default.
+// With collectives running next to backward they are a loss — 3.570 vs 3.349 ms/step at 2 GPUs (profiles/r2_step_sweeps.md):
+// the early-launched CTAs of the next kernel sit on the SM slots the collective's CTAs need — so the multi-GPU policies
+// switch them off (ops.set_pdl, unless TDS_PDL is set explicitly).  The griddepcontrol instructions are no-ops without the edge.
+inline int& pdl_flag() {
+  static int on = !(getenv("TDS_PDL") && atoi(getenv("TDS_PDL")) == 0);
   return on;
 }
+inline bool pdl_enabled() { return pdl_flag() != 0; }
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

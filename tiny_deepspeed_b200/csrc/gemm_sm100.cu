@@ -40,8 +40,8 @@ constexpr int kThreads = 192;        // single pipeline: producer, issuer, 4 epi
 // Epilogue warps: 4 (one per TMEM lane quadrant), or 8 on the FAST (bf16 TMA-store) kernels — two warps per quadrant, each
 // taking 32 of a slab's 64 columns.  At one tile per CTA the epilogue is pure critical path, and with one warp per scheduler
 // it ran at ~1/3 instruction per cycle (profiles/r2_gemm_epitrace_before.log: 1900 cycles for a 128 x 64 tile).
-constexpr int epi_warps(bool fast) { return fast ? 8 : 4; }
-constexpr int gemm_threads(int np, bool fast) { return 32 * (2 * np + epi_warps(fast)); }
+constexpr int epi_warps(int fast) { return fast == 2 ? 8 : 4; }
+constexpr int gemm_threads(int np, int fast) { return 32 * (2 * np + epi_warps(fast)); }
 constexpr uint32_t kStageBufBytes = 4096;   // one 32-row x 64-col bf16 slab, SWIZZLE_128B
 
 enum { EPI_NONE = 0, EPI_GELU_SAVE = 1, EPI_GELU_BWD = 2, EPI_RESIDUAL = 3 };
@@ -126,7 +126,7 @@ __device__ __forceinline__ float ld1_any(const void* base, long long idx, int f3
 // EPI  = epilogue functor fixed at compile time (EPI_*), or -1: read g.epi at run time (generic instantiations)
 // FAST = the output goes registers -> swizzled smem -> TMA store and nothing else is compiled in (bf16 out, aligned, no
 //        accumulate: every GEMM of the bf16 training step); the generic instantiations keep the direct-store paths
-template <int BN, bool F32, bool RED, int NP, int EPI, bool FAST>
+template <int BN, bool F32, bool RED, int NP, int EPI, int FAST>   // FAST: 0 generic, 1 = bf16 TMA-store path, 2 = the same with 8 epilogue warps
 __global__ void __launch_bounds__(gemm_threads(NP, FAST), 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
             const __grid_constant__ CUtensorMap tma_d, const __grid_constant__ CUtensorMap tma_aux,
@@ -796,7 +796,7 @@ static int max_clusters(int cm) {
   return n;
 }
 
-template <int BN, bool F32, bool RED = false, int NP = 1, int EPI = -1, bool FAST = false>
+template <int BN, bool F32, bool RED = false, int NP = 1, int EPI = -1, int FAST = 0>
 static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const CUtensorMap& tx,
                    const GemmDev& g, int tiles, cudaStream_t s) {
   static bool attr_done = false;
@@ -923,17 +923,27 @@ void gemm_bf16(const GemmParams& p, cudaStream_t stream) {
     else TDS_L(192, F32_, RED_, 1, EPI_, FAST_);                                                 \
   } while (0)
   if (p.reduce_out) {
-    TDS_BY_BN(false, true, -1, false);
+    TDS_BY_BN(false, true, -1, 0);
   } else if (f32) {
-    TDS_BY_BN(true, false, -1, false);
+    TDS_BY_BN(true, false, -1, 0);
   } else if (g.tma_store && (g.aux_tma || g.epi == EPI_NONE || g.epi == EPI_GELU_SAVE)) {
     // the bf16 training step lives here: epilogue functor and store path fixed at compile time
-    if (g.epi == EPI_NONE) TDS_BY_BN(false, false, EPI_NONE, true);
-    else if (g.epi == EPI_GELU_SAVE) TDS_BY_BN(false, false, EPI_GELU_SAVE, true);
-    else if (g.epi == EPI_GELU_BWD) TDS_BY_BN(false, false, EPI_GELU_BWD, true);
-    else TDS_BY_BN(false, false, EPI_RESIDUAL, true);
+    // TDS_GEMM_EPI_WARPS=8: two epilogue warps per TMEM lane quadrant.  Faster per GEMM (profiles/r2_gemm_epi_8warps.log) but the
+    // CTA then owns ~62 K of the SM's 64 K registers, so no collective CTA can share the SM: default 4
+    static const bool ew8 = getenv("TDS_GEMM_EPI_WARPS") && atoi(getenv("TDS_GEMM_EPI_WARPS")) == 8;
+    if (ew8) {
+      if (g.epi == EPI_NONE) TDS_BY_BN(false, false, EPI_NONE, 2);
+      else if (g.epi == EPI_GELU_SAVE) TDS_BY_BN(false, false, EPI_GELU_SAVE, 2);
+      else if (g.epi == EPI_GELU_BWD) TDS_BY_BN(false, false, EPI_GELU_BWD, 2);
+      else TDS_BY_BN(false, false, EPI_RESIDUAL, 2);
+    } else {
+      if (g.epi == EPI_NONE) TDS_BY_BN(false, false, EPI_NONE, 1);
+      else if (g.epi == EPI_GELU_SAVE) TDS_BY_BN(false, false, EPI_GELU_SAVE, 1);
+      else if (g.epi == EPI_GELU_BWD) TDS_BY_BN(false, false, EPI_GELU_BWD, 1);
+      else TDS_BY_BN(false, false, EPI_RESIDUAL, 1);
+    }
   } else {
-    TDS_BY_BN(false, false, -1, false);
+    TDS_BY_BN(false, false, -1, 0);
   }
 #undef TDS_BY_BN
 #undef TDS_L

@@ -37,6 +37,7 @@ struct GemmParams {
   const void* prefetch = nullptr;  int64_t prefetch_bytes = 0;
 };
 void gemm_bf16(const GemmParams& p, cudaStream_t stream);
+void set_pdl_enabled(bool on);   // programmatic-dependent-launch edges between our kernels (common.cuh); optim.cu
 // EXPERIMENTAL CTA-pair (cta_group::2) variant, gemm2_sm100.cu: returns false without launching when the problem is outside
 // its coverage (then call gemm_bf16).  Opt-in through TDS_GEMM_2CTA=1 in the binding.
 bool gemm2_bf16(const GemmParams& p, cudaStream_t stream);

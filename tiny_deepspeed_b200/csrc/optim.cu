@@ -9,6 +9,8 @@
 
 namespace tds {
 
+void set_pdl_enabled(bool on) { pdl_flag() = on ? 1 : 0; }
+
 __global__ void step_inc_kernel(int* p) {
   pdl_launch(); pdl_wait(); *p += 1; }
 void step_increment(int* step_ptr, cudaStream_t s) { launch_k(step_inc_kernel, dim3(1), dim3(1), 0, s, step_ptr); }

@@ -98,6 +98,15 @@ def gemm(a: torch.Tensor, b: torch.Tensor, *, a_mn: bool = False, b_mn: bool = F
     return out
 
 
+def set_pdl(on: bool, force: bool = False):
+    """Programmatic-dependent-launch edges between our kernels.  Default: on (single GPU); the multi-GPU policies call
+    ``set_pdl(False)`` because the early-launched CTAs take the SM slots their collectives need (csrc/common.cuh).  An explicit
+    ``TDS_PDL`` in the environment wins unless ``force``.  Takes effect for kernels launched (or captured) afterwards."""
+    if ("TDS_PDL" in os.environ and not force) or not torch.cuda.is_available() or is_forced_torch():
+        return
+    ext().set_pdl(bool(on))
+
+
 _L2_PREFETCH = os.environ.get("TDS_L2_PREFETCH", "1") != "0"
 _L2_PREFETCH_MAX = 16 << 20
 

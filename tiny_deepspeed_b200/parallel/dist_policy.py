@@ -30,6 +30,9 @@ class DistPolicy(CommPolicy):
         self.average = average
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world > 1 and torch.cuda.is_available():
+            from .. import ops as _ops
+            _ops.set_pdl(False)      # NCCL kernels run next to backward (see NativePolicy)
         self.pending = deque()
         self.window = window  # ZeRO-2/3: max non-owner gradients alive at once
         self.stats = {"collectives": 0, "bytes": 0}

@@ -64,6 +64,9 @@ class NativePolicy(CommPolicy):
         self.average = average
         self.scale = 1.0 / self.world if average else 1.0
         import os
+        if self.world > 1:
+            from .. import ops as _ops
+            _ops.set_pdl(False)      # collectives run next to backward: no early-launched CTAs on the SM slots they need
         if os.environ.get("TDS_BUCKET_MB"):
             bucket_bytes = int(float(os.environ["TDS_BUCKET_MB"]) * (1 << 20))
         if os.environ.get("TDS_COMM_BLOCKS"):
