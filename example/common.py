@@ -30,6 +30,8 @@ def parse_args(mode):
     ap.add_argument("--backend", default="auto", choices=["auto", "native", "dist"])
     ap.add_argument("--partition", default="greedy", choices=["greedy", "contiguous", "balanced"])
     ap.add_argument("--quiet-partition", action="store_true")
+    ap.add_argument("--time", action="store_true",
+                    help="device-time every step (utils.StepTimer: CUDA events around the step, one sync per step) and print a summary line")
     return ap.parse_args()
 
 
@@ -68,9 +70,15 @@ def train_loop(model, optimizer, x, y, args, rank=0, distributed=False):
     """``--graph`` replays the whole step as one CUDA graph; either way the step goes through TrainStep, which also carries the
     optional watchdog (TDS_WATCHDOG_S) and JSON-lines metrics (TDS_METRICS / TDS_METRICS_EVERY)."""
     from tiny_deepspeed_b200 import TrainStep
+    from tiny_deepspeed_b200.utils import StepTimer
     step = TrainStep(model, optimizer, use_graph=bool(args.graph))
+    timer = StepTimer(x.device) if getattr(args, "time", False) else None
     for i in range(args.iters):
+        if timer is not None:
+            timer.start()
         loss = step(x, y)                  # eager: model.require_backward_grad_sync re-armed, fwd, bwd, optimizer.step()
+        if timer is not None:
+            timer.stop()
         loss = loss.detach().clone()
         if distributed:
             dist.all_reduce(loss, op=dist.ReduceOp.SUM)
@@ -78,3 +86,8 @@ def train_loop(model, optimizer, x, y, args, rank=0, distributed=False):
         if rank == 0:
             print(format_loss_line(i, loss.item()), flush=True)
     step.finish()
+    if timer is not None and rank == 0 and timer.samples_ms:
+        tail = timer.samples_ms[len(timer.samples_ms) // 2:]          # second half: past warm-up / graph capture
+        ms = sum(tail) / len(tail)
+        ntok = int(x.numel()) * (dist.get_world_size() if distributed else 1)
+        print(f"timing: {ms:.3f} ms/step over the last {len(tail)} steps, {ntok / (ms * 1e-3):.0f} tokens/s", flush=True)

@@ -36,3 +36,12 @@ def test_distributed_examples_cpu_gloo(mode):
     assert r.returncode == 0, (r.stdout[-1500:], r.stderr[-2500:])
     losses = _losses(r.stdout)
     assert losses[-1] < losses[0]
+
+
+def test_single_device_example_time_flag_prints_summary():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "example", "single_device", "train.py"), "--device", "cpu",
+                          "--model", "tiny", "--iters", "4", "--time"], capture_output=True, text=True, timeout=300, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert sum(l.startswith("iter ") for l in lines) == 4
+    assert lines[-1].startswith("timing: ") and "ms/step" in lines[-1] and "tokens/s" in lines[-1]

@@ -133,3 +133,34 @@ def test_optimizer_step_count_roundtrip_matches_device_counter():
     opt2._step_dev = torch.tensor([0], dtype=torch.int32)
     opt2.load_state_dict(sd | {"step": 7})
     assert opt2.step_count == 7 and int(opt2._step_dev.item()) == 7
+
+
+def test_prefetch_chain_registers_nothing_and_follows_forward_order():
+    """The L2 prefetch chain (nn.modules.link_prefetch_chain) stores module references outside nn.Module's registries: parameter
+    names / order — the compatibility contract with the reference's model — and the state dict are unchanged."""
+    from tiny_deepspeed_b200.models.gpt2 import GPT2Model, gpt2_config
+    model = GPT2Model(gpt2_config("tiny"))
+    names = [n for n, _ in model.named_parameters()]
+    assert len(names) == len(set(names))
+    assert not any("_pf_" in n for n in names)
+    assert not any("_pf_" in k for k in model.state_dict())
+    blk0, blk1 = model.transformer.h[0], model.transformer.h[1]
+    chain = [blk0.attn.c_attn, blk0.attn.c_proj, blk0.mlp.c_fc, blk0.mlp.c_proj, blk1.attn.c_attn]
+    for a, b in zip(chain, chain[1:]):
+        assert a.__dict__["_pf_fwd"] is b and b.__dict__["_pf_bwd"] is a
+    last = model.transformer.h[-1].mlp.c_proj
+    assert last.__dict__["_pf_fwd"] is model.lm_head and model.lm_head.__dict__["_pf_bwd"] is last
+    assert "_pf_bwd" not in chain[0].__dict__ and "_pf_fwd" not in model.lm_head.__dict__
+    # number of registered submodules is what the architecture defines (nothing sneaked in through the chain)
+    n_linear = sum(1 for m in model.modules() if m.__class__.__name__ == "Linear")
+    assert n_linear == 4 * len(model.transformer.h) + 1
+
+
+def test_gpu_only_switches_are_noops_on_cpu():
+    """ops.prefetch_next / ops.set_pdl must not touch the extension on a CPU box (the CPU suite runs without a GPU)."""
+    import torch
+    from tiny_deepspeed_b200 import ops
+    ops.prefetch_next(torch.zeros(64))
+    ops.prefetch_next(None)
+    ops.set_pdl(False)
+    ops.set_pdl(True, force=True)

@@ -10,7 +10,7 @@ supported_acc_dtypes = {
     torch.int8: torch.int32,
 }
 
-# dtypes the sm_100a kernels accept for activations / parameters (GEMM operands are bf16 only)
+# dtypes the sm_100a kernels accept for activations / parameters (bf16 -> kind::f16 GEMMs, fp32 -> kind::tf32 GEMMs on the fp32 tensors in place)
 kernel_dtypes = (torch.bfloat16, torch.float32)
 
 
