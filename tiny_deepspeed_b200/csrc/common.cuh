@@ -104,9 +104,9 @@ template <typename T> TDS_DEVICE void stf(T* p, float v);
 template <> TDS_DEVICE void stf<float>(float* p, float v) { *p = v; }
 template <> TDS_DEVICE void stf<__nv_bfloat16>(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
 
-// One MUFU instruction (max relative error ~2^-11, well inside bf16's 2^-8 rounding of every value it feeds) instead of
-// tanhf's ~40-instruction two-branch sequence: the GELU epilogues run on the GEMM's 4 epilogue warps only, 192 elements per
-// thread for a 128 x 192 tile, and were issue-bound on exactly that sequence (profiles/r2_timeline.md).
+// One MUFU instruction (max relative error ~2^-11, well inside bf16's 2^-8 rounding of every value it feeds), spelled out
+// instead of relying on --use_fast_math to turn tanhf into it: the GELU epilogues run on the GEMM's 4 epilogue warps only,
+// 192 elements per thread for a 128 x 192 tile, where every instruction is on the critical path (profiles/r2_gemm_epilogue.md).
 TDS_DEVICE float tanh_fast(float x) { float y; asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 TDS_DEVICE float gelu_tanh(float x) {
   const float k0 = 0.7978845608028654f, k1 = 0.044715f;

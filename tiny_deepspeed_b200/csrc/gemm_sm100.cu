@@ -830,7 +830,7 @@ static void launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorM
 // cluster size along M: B-tile multicast divides L2->SM (or NVLink, for a ZeRO-3 peer weight) operand traffic by cm
 static int pick_cluster(const GemmParams& p, int bn) {
   static const int env = getenv("TDS_GEMM_CM") ? atoi(getenv("TDS_GEMM_CM")) : -1;
-  // measured on B200 (profiles/r1_gemm_cluster_sweep.md): at M = 1024 the GPT-2 GEMMs are latency-, not L2-bound, and
+  // measured on B200 (profiles/r1_overlap_pdl.md): at M = 1024 the GPT-2 GEMMs are latency-, not L2-bound, and
   // cluster launch costs more than the multicast saves -> off unless requested
   int want = p.cluster_m > 0 ? p.cluster_m : (env >= 0 ? env : 1);
   if (want <= 1 || p.tri != 0 || p.batch != 1 || p.in_dtype == kF32 || p.reduce_out) return 1;
