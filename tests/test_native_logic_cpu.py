@@ -250,3 +250,39 @@ def test_bucket_runs_merge_adjacent_tensors_of_one_owner():
                 assert all(table[n] == o for n in names)
     finally:
         mp.undo()
+
+
+def test_flash_backward_work_split_covers_every_step_once():
+    """Host-side model of flash_bwd_kernel's work mapping (csrc/flash_sm100.cu): key block jb meets the query blocks i >= jb;
+    blocks with more than ceil(nq / 2) steps are cut into two CTAs.  Every (jb, i) pair must be covered exactly once, no CTA
+    may be empty, and the longest CTA has ceil(nq / 2) steps (the point of the split)."""
+    def cta(x, nq):
+        n_split = nq - (nq + 1) // 2
+        if x < 2 * n_split:
+            jb = x >> 1
+            n_all = nq - jb
+            h0 = (n_all + 1) // 2
+            it0, n_it = (h0, n_all - h0) if x & 1 else (0, h0)
+            return jb, it0, n_it, True
+        jb = x - n_split
+        return jb, 0, nq - jb, False
+
+    for nq in range(1, 33):
+        n_split = nq - (nq + 1) // 2
+        seen, longest = {}, 0
+        for x in range(nq + n_split):
+            jb, it0, n_it, split = cta(x, nq)
+            assert 0 <= jb < nq and n_it >= 1, (nq, x)
+            assert split == (jb < n_split)
+            longest = max(longest, n_it)
+            for it in range(it0, it0 + n_it):
+                i = jb + it
+                assert jb <= i < nq
+                assert (jb, i) not in seen, (nq, jb, i)
+                seen[(jb, i)] = x
+        assert len(seen) == nq * (nq + 1) // 2
+        assert longest == (nq + 1) // 2
+        # the diagonal step (i == jb, the only masked one) always belongs to the CTA that starts at it0 == 0
+        for jb in range(nq):
+            x = seen[(jb, jb)]
+            assert cta(x, nq)[1] == 0
